@@ -1,0 +1,63 @@
+"""In-tree build of the CUDA engine (nvcc, sm_100a).  Used by __graft_entry__.build() and by userfunc.py for
+scene-specialised variants that inline user callables as device functions."""
+from __future__ import annotations
+
+import concurrent.futures
+import hashlib
+import os
+import pathlib
+import subprocess
+
+PKG = pathlib.Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+SOURCES = ["otb_api.cu", "otb_trace.cu", "otb_render.cu", "otb_detect.cu", "otb_gen.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-fmad=false",           # op-for-op parity with the reference's numpy arithmetic
+              "-Xcompiler", "-fPIC", f"-I{ROOT / 'include'}", f"-I{CSRC}"]
+
+
+def nvcc() -> str:
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc"):
+        if c and pathlib.Path(c).exists():
+            return c
+    return "nvcc"
+
+
+def source_digest() -> str:
+    h = hashlib.sha256()
+    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "otb.h"]):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS[:8]).encode())
+    return h.hexdigest()
+
+
+def build_library(out_path=None, extra_flags=(), force=False, objdir=None, sources=None) -> pathlib.Path:
+    """Compiles the engine sources in parallel and links a shared library."""
+    out_path = pathlib.Path(out_path) if out_path else CSRC / "libotb.so"
+    objdir = pathlib.Path(objdir) if objdir else CSRC / "build"
+    objdir.mkdir(parents=True, exist_ok=True)
+    stamp = objdir / (out_path.name + ".digest")
+    digest = source_digest() + "|" + " ".join(extra_flags)
+    if not force and out_path.exists() and stamp.exists() and stamp.read_text() == digest:
+        return out_path
+    cc = nvcc()
+    srcs = list(sources or SOURCES)
+
+    def compile_one(src):
+        obj = objdir / (src.replace(".cu", ".o"))
+        r = subprocess.run([cc, *NVCC_FLAGS, *extra_flags, "-c", str(CSRC / src), "-o", str(obj)],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    r = subprocess.run([cc, "-shared", "-o", str(out_path), *[str(o) for o in objs], "-lcudart"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    stamp.write_text(digest)
+    return out_path

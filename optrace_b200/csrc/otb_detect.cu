@@ -1,0 +1,233 @@
+// otb_detect.cu — detector path: hit finding on stored ray sections (Raytracer._hit_detector,
+// raytracer.py:881-1051) and XYZW histogram binning (RenderImage.render, render_image.py:390-417,
+// misc.binning_indices_2d, misc.py:59-91, CIE observers, observers.py:14-41).
+#include "otb_common.cuh"
+#include "otb_surfaces.cuh"
+#include "otb_media.cuh"
+#include "otb_observers.cuh"
+#include "otb_bin.cuh"
+
+// atomic min / max on doubles through compare-and-swap (one call per block)
+__device__ __forceinline__ void atomic_min_d(double* addr, double v)
+{
+    unsigned long long* a = (unsigned long long*)addr;
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        if (!(v < __longlong_as_double((long long)assumed))) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (assumed != old);
+}
+__device__ __forceinline__ void atomic_max_d(double* addr, double v)
+{
+    unsigned long long* a = (unsigned long long*)addr;
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        if (!(v > __longlong_as_double((long long)assumed))) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (assumed != old);
+}
+
+struct DetArgs {
+    OtbRayStore st;
+    OtbDetector det;
+    int64_t begin, end;
+    double* hx;
+    double* hy;
+    float* hw;
+    double* range;           // [4] min x, max x, min y, max y
+    unsigned long long* ill;
+    int* status;
+};
+
+__global__ void __launch_bounds__(128) detector_hits_kernel(const DetArgs a)
+{
+    const int64_t N = a.st.N;
+    const int nt = a.st.nt;
+    const int64_t Nnt = N*(int64_t)nt;
+    const double* __restrict__ P = a.st.p_d;
+    const float* __restrict__ Wt = a.st.w_d;
+    const OtbSurface& S = a.det.surface;
+    const int64_t ray = a.begin + (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+    const bool valid = ray < a.end;
+
+    float w = 0.0f;
+    double X = 0.0, Y = 0.0;
+    bool ill = false, ok = false;
+    if (valid) {
+        // section straddling the detector z-extent (raytracer.py:929-938)
+        bool no_start = true, no_reach = true;
+        int first_ge = -1;
+        for (int j = 0; j < nt; ++j) {
+            const double z = P[ray + N*(int64_t)j + 2*Nnt];
+            const bool bmin = z >= S.z_min, bmax = z >= S.z_max;
+            no_start = no_start && (bmin && bmax);
+            no_reach = no_reach && (!bmin && !bmax);
+            if (first_ge < 0 && bmin) first_ge = j;
+        }
+        if (!(no_start || no_reach)) {
+            int sec = (first_ge < 0 ? 0 : first_ge) - 1;
+            if (sec < 0) sec = 0;
+            HitResult h;
+            h.hit = false;
+            h.p = v3(0, 0, 0);
+            bool more = true;
+            while (more) {
+                // rays_by_mask (ray_storage.py:235-293): direction from position differences, normalised
+                const int s1 = (sec < nt - 1) ? sec + 1 : sec;
+                const int64_t o0 = ray + N*(int64_t)sec, o1 = ray + N*(int64_t)s1;
+                const V3 p = v3(P[o0], P[o0 + Nnt], P[o0 + 2*Nnt]);
+                const V3 s = unit3(v3(P[o1] - p.x, P[o1 + Nnt] - p.y, P[o1 + 2*Nnt] - p.z));
+                w = Wt[o0];
+                ++sec;
+                if (sec >= nt) {          // ray ends at the outline: no intersection (raytracer.py:970-978)
+                    w = 0.0f;
+                    break;
+                }
+                h = surf_find_hit(S, nullptr, p, s, a.status);
+                ill = ill || h.ill;
+                const double p2z = P[ray + N*(int64_t)sec + 2*Nnt];
+                more = h.p.z > p2z + OTB_C_EPS;      // hit behind the next stored point -> try next section
+            }
+            if (h.hit && w > 0.0f) {
+                X = h.p.x;
+                Y = h.p.y;
+                sphere_project(S, a.det.projection, X, Y, h.p.z);
+                ok = true;
+                if (a.det.has_extent) {
+                    const double* e = a.det.extent;
+                    ok = (e[0] <= X) && (X <= e[1]) && (e[2] <= Y) && (Y <= e[3]);
+                }
+            }
+        }
+        const int64_t k = ray - a.begin;
+        a.hx[k] = X;
+        a.hy[k] = Y;
+        a.hw[k] = ok ? w : 0.0f;
+    }
+
+    // block reduction of the hit range (auto extent, raytracer.py:1042-1046) and the ill counter
+    __shared__ double smin_x[4], smax_x[4], smin_y[4], smax_y[4];
+    __shared__ int sill;
+    if (threadIdx.x == 0) sill = 0;
+    double mnx = ok ? X : INFINITY, mxx = ok ? X : -INFINITY, mny = ok ? Y : INFINITY, mxy = ok ? Y : -INFINITY;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, d));
+        mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+        mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, d));
+        mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { smin_x[warp] = mnx; smax_x[warp] = mxx; smin_y[warp] = mny; smax_y[warp] = mxy; }
+    __syncthreads();
+    unsigned bi = __ballot_sync(0xffffffffu, ill);
+    if (bi && (threadIdx.x & 31) == 0) atomicAdd(&sill, __popc(bi));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+            mnx = fmin(smin_x[0], smin_x[k]); smin_x[0] = mnx;
+            mxx = fmax(smax_x[0], smax_x[k]); smax_x[0] = mxx;
+            mny = fmin(smin_y[0], smin_y[k]); smin_y[0] = mny;
+            mxy = fmax(smax_y[0], smax_y[k]); smax_y[0] = mxy;
+        }
+        if (smin_x[0] <= smax_x[0]) {
+            atomic_min_d(&a.range[0], smin_x[0]);
+            atomic_max_d(&a.range[1], smax_x[0]);
+            atomic_min_d(&a.range[2], smin_y[0]);
+            atomic_max_d(&a.range[3], smax_y[0]);
+        }
+        if (sill) atomicAdd(a.ill, (unsigned long long)sill);
+    }
+}
+
+__global__ void __launch_bounds__(256) render_kernel(BinGrid g, const double* __restrict__ obs, int64_t M,
+                                                     const double* __restrict__ x, const double* __restrict__ y,
+                                                     const float* __restrict__ w, const float* __restrict__ wl,
+                                                     double* __restrict__ img, int* __restrict__ cnt)
+{
+    for (int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x*blockDim.x) {
+        const float wi = w[i];
+        if (!(wi > 0.0f)) continue;            // only rays with a valid hit reach RenderImage.render
+        accumulate_hit(g, obs, x[i], y[i], wi, wl[i], img, cnt);
+    }
+}
+
+static double* g_obs_d = nullptr;
+int otb_sm_count();
+
+int otb_observer_table(const double** out)
+{
+    if (!g_obs_d) {
+        OTB_CUDA(cudaMalloc(&g_obs_d, sizeof(OTB_OBSERVERS)));
+        OTB_CUDA(cudaMemcpy(g_obs_d, OTB_OBSERVERS, sizeof(OTB_OBSERVERS), cudaMemcpyHostToDevice));
+    }
+    *out = g_obs_d;
+    return OTB_OK;
+}
+
+BinGrid otb_make_grid(const double extent[4], int Nx, int Ny)
+{
+    BinGrid g;
+    g.e0 = extent[0]; g.e1 = extent[1]; g.e2 = extent[2]; g.e3 = extent[3];
+    g.Nx = Nx; g.Ny = Ny;
+    g.fx = (double)Nx/(extent[1] - extent[0]);
+    g.fy = (double)Ny/(extent[3] - extent[2]);
+    return g;
+}
+
+extern "C" {
+
+int otb_detector_hits(const OtbRayStore* store, int64_t ray_begin, int64_t ray_end, const OtbDetector* det_h,
+                      double* hx_d, double* hy_d, float* hw_d, double* range_d, int64_t* ill_d, void* stream)
+{
+    if (!store || !det_h || !hx_d || !hy_d || !hw_d || !range_d || !ill_d) { otb_set_error("null argument"); return OTB_ERR_INVALID_ARG; }
+    if (ray_begin < 0 || ray_end > store->N || ray_begin > ray_end) { otb_set_error("invalid ray range"); return OTB_ERR_INVALID_ARG; }
+    const int k = det_h->surface.kind;
+    if (k == OTB_SURF_FUNC || k == OTB_SURF_DATA || k == OTB_SURF_ASPHERE) {
+        otb_set_error("Function/Data surfaces are not supported as detector surfaces (detector.py:37-41)");
+        return OTB_ERR_UNSUPPORTED;
+    }
+    const int64_t n = ray_end - ray_begin;
+    if (n == 0) return OTB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DetArgs a;
+    a.st = *store;
+    a.det = *det_h;
+    a.begin = ray_begin;
+    a.end = ray_end;
+    a.hx = hx_d; a.hy = hy_d; a.hw = hw_d;
+    a.range = range_d;
+    a.ill = (unsigned long long*)ill_d;
+    int* status_d;
+    OTB_CUDA(cudaMalloc(&status_d, sizeof(int)));
+    OTB_CUDA(cudaMemsetAsync(status_d, 0, sizeof(int), st));
+    a.status = status_d;
+    detector_hits_kernel<<<(unsigned)((n + 127)/128), 128, 0, st>>>(a);
+    OTB_CUDA(cudaGetLastError());
+    int status = 0;
+    OTB_CUDA(cudaMemcpyAsync(&status, status_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OTB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(status_d);
+    if (status & OTB_STATUS_TIMEOUT) { otb_set_error("Timeout after 200 iterations in hit finding."); return OTB_ERR_NUMERIC_TIMEOUT; }
+    return OTB_OK;
+}
+
+int otb_render_xyzw(const double* x_d, const double* y_d, const float* w_d, const float* wl_d, int64_t M,
+                    const double extent[4], int32_t Nx, int32_t Ny, double* img_d, int32_t* cnt_d, void* stream)
+{
+    if (!extent || !img_d) { otb_set_error("null argument"); return OTB_ERR_INVALID_ARG; }
+    if (Nx <= 0 || Ny <= 0 || !(extent[1] > extent[0]) || !(extent[3] > extent[2])) { otb_set_error("invalid image grid"); return OTB_ERR_INVALID_ARG; }
+    if (M <= 0) return OTB_OK;
+    if (!x_d || !y_d || !w_d || !wl_d) { otb_set_error("null argument"); return OTB_ERR_INVALID_ARG; }
+    const double* obs;
+    if (int rc = otb_observer_table(&obs)) return rc;
+    BinGrid g = otb_make_grid(extent, Nx, Ny);
+    int64_t blocks = (M + 255)/256, cap = (int64_t)otb_sm_count()*8;
+    render_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(g, obs, M, x_d, y_d, w_d, wl_d, img_d, cnt_d);
+    OTB_CUDA(cudaGetLastError());
+    return OTB_OK;
+}
+
+}  // extern "C"

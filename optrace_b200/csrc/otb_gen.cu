@@ -1,0 +1,337 @@
+// otb_gen.cu — on-device ray generation: RaySource.create_rays (ray_source.py:204-437) with the
+// sampling primitives of random.py (stratified grids + shuffle, Shirley disc map, inverse-CDF tables),
+// driven by counter-based Philox4x32-10 instead of numpy's SFC64 stream.
+//
+// Stratification: the reference draws "grid cell + dither" and then shuffles globally (random.py:25-45).
+// Here ray m of a source takes grid cell perm_key(m), a keyed Feistel bijection of [0, n) (otb_rng.cuh), so
+// every cell is used exactly once and different random variables are decorrelated by different keys.
+// Generated bundles therefore agree with the reference statistically (same distributions, same
+// stratification), not bit-wise; parity tests inject reference-generated bundles instead.
+#include "otb_common.cuh"
+#include "otb_rng.cuh"
+
+#define OTB_STATUS_NEG_DIR 8    // a generated direction has s_z <= 0 (ray_source.py:353-354)
+
+struct GenCtx {
+    uint64_t seed;
+    uint64_t gid;      // global ray id (Philox counter)
+    uint64_t m;        // index of the ray inside its source
+    uint64_t n;        // rays of this source in this launch
+    uint32_t src;      // source index (decorrelates sources)
+};
+
+enum { ST_POS = 1, ST_WL = 2, ST_RGB = 3, ST_DIV = 4, ST_DIV2 = 5, ST_POL = 6, ST_PIX = 7, ST_PIXOFF = 8 };
+
+__device__ __forceinline__ Philox4 draw(const GenCtx& g, uint32_t stream) { return philox4x32_10(g.gid, stream, g.src, g.seed); }
+__device__ __forceinline__ uint64_t stratum(const GenCtx& g, uint32_t stream)
+{
+    return feistel_perm(g.m, g.n, g.seed ^ ((uint64_t)stream << 40) ^ ((uint64_t)g.src << 20) ^ 0x5bd1e995u);
+}
+
+// random.stratified_interval_sampling (random.py:48-66): value in [a, b)
+__device__ __forceinline__ double strat1(const GenCtx& g, uint32_t stream, double a, double b)
+{
+    Philox4 r = draw(g, stream);
+    double dba = (b - a)/(double)g.n;
+    return a + ((double)stratum(g, stream) + u01(r.v[0], r.v[1]))*dba;
+}
+
+// random.stratified_rectangle_sampling (random.py:8-45)
+__device__ __forceinline__ void strat2(const GenCtx& g, uint32_t stream, double a, double b, double c, double d, double& x, double& y)
+{
+    Philox4 r = draw(g, stream);
+    double u1 = u01(r.v[0], r.v[1]), u2 = u01(r.v[2], r.v[3]);
+    uint64_t N2 = (uint64_t)sqrt((double)g.n);
+    while (N2*N2 > g.n) --N2;
+    while ((N2 + 1)*(N2 + 1) <= g.n) ++N2;
+    uint64_t j = stratum(g, stream);
+    if (j < N2*N2) {
+        uint64_t iy = j/N2, ix = j - iy*N2;
+        x = a + ((double)ix + u1)*((b - a)/(double)N2);
+        y = c + ((double)iy + u2)*((d - c)/(double)N2);
+    } else {            // remaining N - N2^2 samples are plain uniform (random.py:36-37)
+        x = a + u1*(b - a);
+        y = c + u2*(d - c);
+    }
+}
+
+// random.stratified_ring_sampling (random.py:70-110): Shirley equal-area map + disc->annulus map
+__device__ __forceinline__ void strat_ring(const GenCtx& g, uint32_t stream, double ri, double r, bool polar, double& o1, double& o2)
+{
+    double x, y;
+    strat2(g, stream, -r, r, -r, r, x, y);
+    double x2 = x*x, y2 = y*y, r_ = 0.0, theta = 0.0;
+    if (x2 > y2) {
+        r_ = x;
+        theta = 0.7853981633974483*y/x;
+    } else if (y2 > 0) {
+        r_ = y;
+        theta = 1.5707963267948966 - 0.7853981633974483*x/y;
+    }
+    if (ri != 0.0) {
+        double q = ri/r;
+        double v = sqrt(ri*ri + r_*r_*(1 - q*q));
+        r_ = (r_ < 0) ? -v : v;
+    }
+    if (!polar) {
+        o1 = r_*cos(theta);
+        o2 = r_*sin(theta);
+    } else {
+        if (r_ < 0) theta -= 3.141592653589793;
+        o1 = fabs(r_);
+        o2 = theta;
+    }
+}
+
+// continuous inverse CDF with linear interpolation (random.py:143-157; scipy interp1d kind="linear")
+__device__ inline double icdf_linear(const double* __restrict__ x, const double* __restrict__ F, int n, double X)
+{
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (X >= F[mid]) lo = mid; else hi = mid;
+    }
+    double dF = F[lo + 1] - F[lo];
+    if (!(dF > 0)) return x[lo];
+    return x[lo] + (X - F[lo])/dF*(x[lo + 1] - x[lo]);
+}
+
+// discrete inverse CDF (random.py:129-140; interp1d kind="next"): first index with F[i] >= X
+__device__ inline int icdf_next(const double* __restrict__ F, int n, double X)
+{
+    int lo = -1, hi = n - 1;       // F[hi] >= X by construction (X <= F[n-1])
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (F[mid] >= X) hi = mid; else lo = mid;
+    }
+    return hi;
+}
+
+__global__ void __launch_bounds__(128)
+generate_kernel(const OtbSource* __restrict__ srcs, int nsrc, const double* __restrict__ aux, int64_t N, uint64_t seed,
+                int64_t ray_offset, int no_pol, double* __restrict__ p0, double* __restrict__ s0, float* __restrict__ pol0,
+                float* __restrict__ w0, float* __restrict__ wl0, int* status)
+{
+    for (int64_t k = (int64_t)blockIdx.x*blockDim.x + threadIdx.x; k < N; k += (int64_t)gridDim.x*blockDim.x) {
+        int si = 0;
+        for (int j = 1; j < nsrc; ++j) if (k >= srcs[j].ray_start) si = j;
+        const OtbSource& S = srcs[si];
+        GenCtx g;
+        g.seed = seed;
+        g.gid = (uint64_t)(ray_offset + k);
+        g.m = (uint64_t)(k - S.ray_start);
+        g.n = (uint64_t)S.n_rays;
+        g.src = (uint32_t)si;
+
+        // ---- position (circular_surface.py:32-43, ring_surface.py:135-148, rectangular_surface.py:144-159,
+        //      line.py:81-96, point.py:62-69, image sources ray_source.py:237-255)
+        double px = S.pos[0], py = S.pos[1];
+        const double pz = S.pos[2];
+        int pix = -1;
+        switch (S.shape) {
+        case OTB_SHAPE_POINT: break;
+        case OTB_SHAPE_LINE: {
+            double t = strat1(g, ST_POS, -S.geom[0], S.geom[0]);
+            px = S.pos[0] + S.geom[1]*t;
+            py = S.pos[1] + S.geom[2]*t;
+            break;
+        }
+        case OTB_SHAPE_CIRCLE:
+        case OTB_SHAPE_RING: {
+            double x, y;
+            strat_ring(g, ST_POS, S.geom[0], S.geom[1], false, x, y);
+            px += x;
+            py += y;
+            break;
+        }
+        case OTB_SHAPE_RECT: {
+            double x, y;
+            strat2(g, ST_POS, -S.geom[0]/2, S.geom[0]/2, -S.geom[1]/2, S.geom[1]/2, x, y);
+            if (S.geom[4] != 0.0) {
+                double xr = x*S.geom[2] - y*S.geom[3], yr = x*S.geom[3] + y*S.geom[2];
+                x = xr;
+                y = yr;
+            }
+            px += x;
+            py += y;
+            break;
+        }
+        default: {   // image sources: pixel by discrete inverse CDF of pixel power, uniform offset inside the pixel
+            if (S.img_w*S.img_h > 1) {
+                const double* idx = aux + S.pix_cdf_off;
+                const double* F = idx + S.pix_cdf_n;
+                double X = strat1(g, ST_PIX, 0.0, F[S.pix_cdf_n - 1]);
+                pix = (int)idx[icdf_next(F, S.pix_cdf_n, X)];
+            } else {
+                pix = 0;
+            }
+            int PY = pix/S.img_w, PX = pix - PY*S.img_w;
+            double rx, ry;
+            strat2(g, ST_PIXOFF, 0.0, 1.0, 0.0, 1.0, rx, ry);
+            px = (S.extent[1] - S.extent[0])/(double)S.img_w*((double)PX + rx) + S.extent[0];
+            py = (S.extent[3] - S.extent[2])/(double)S.img_h*((double)PY + ry) + S.extent[2];
+            break;
+        }
+        }
+
+        // ---- wavelength (light_spectrum.py:81-138, srgb.py:513-553)
+        double wl;
+        switch (S.wl_mode) {
+        case OTB_WL_MONO: wl = (double)(float)S.wl[0]; break;
+        case OTB_WL_UNIFORM: wl = strat1(g, ST_WL, S.wl[0], S.wl[1]); break;
+        case OTB_WL_DISCRETE: {
+            const double* x = aux + S.wl_tab_off;
+            const double* F = x + S.wl_tab_n;
+            wl = x[icdf_next(F, S.wl_tab_n, strat1(g, ST_WL, 0.0, F[S.wl_tab_n - 1]))];
+            break;
+        }
+        case OTB_WL_CDF: {
+            const double* x = aux + S.wl_tab_off;
+            const double* F = x + S.wl_tab_n;
+            wl = icdf_linear(x, F, S.wl_tab_n, strat1(g, ST_WL, F[0], F[S.wl_tab_n - 1]));
+            break;
+        }
+        case OTB_WL_GAUSSIAN: {
+            double X = strat1(g, ST_WL, S.wl[2], S.wl[3]);
+            wl = S.wl[0] + 1.4142135623730951*S.wl[1]*erfinv(2*X - 1);
+            break;
+        }
+        default: {   // OTB_WL_SRGB: choose a primary by the pixel's linear-RGB mixing ratios, then its inverse CDF
+            const double* th = aux + S.pix_rgb_off + 2*(int64_t)pix;
+            double c = strat1(g, ST_RGB, 0.0, 1.0);
+            int prim = (c < th[0]) ? 0 : ((c > th[1]) ? 2 : 1);
+            const double* x = aux + S.srgb_off;
+            const double* F = x + 5000*(1 + prim);
+            wl = icdf_linear(x, F, 5000, strat1(g, ST_WL, F[0], F[4999]));
+            break;
+        }
+        }
+
+        // ---- orientation (ray_source.py:264-277)
+        V3 so;
+        if (S.orientation == OTB_OR_CONSTANT) so = v3(S.s[0], S.s[1], S.s[2]);
+        else so = unit3(v3(S.conv_pos[0] - px, S.conv_pos[1] - py, S.conv_pos[2] - pz));
+
+        // ---- divergence (ray_source.py:290-351)
+        V3 s = so;
+        if (S.divergence != OTB_DIV_NONE) {
+            double theta, alpha;
+            if (S.div_2d) {
+                Philox4 r = draw(g, ST_DIV2);
+                // two equally likely half-planes; stratified over the rays like the reference's discrete draw
+                alpha = S.div_axis + ((stratum(g, ST_DIV2) & 1) ? 3.141592653589793 : 0.0);
+                (void)r;
+                if (S.divergence == OTB_DIV_LAMBERTIAN) theta = asin(strat1(g, ST_DIV, 0.0, S.div_sin));
+                else if (S.divergence == OTB_DIV_ISOTROPIC) theta = strat1(g, ST_DIV, 0.0, S.div_angle);
+                else {
+                    const double* x = aux + S.div_tab_off;
+                    const double* F = x + S.div_tab_n;
+                    theta = icdf_linear(x, F, S.div_tab_n, strat1(g, ST_DIV, F[0], F[S.div_tab_n - 1]));
+                }
+            } else {
+                double rr;
+                strat_ring(g, ST_DIV, 0.0, S.div_sin, true, rr, alpha);
+                if (S.divergence == OTB_DIV_LAMBERTIAN) theta = asin(rr);
+                else if (S.divergence == OTB_DIV_ISOTROPIC) theta = acos(1 - rr*rr);
+                else {
+                    const double* x = aux + S.div_tab_off;
+                    const double* F = x + S.div_tab_n;
+                    double X0 = rr*rr/(S.div_sin*S.div_sin);
+                    theta = icdf_linear(x, F, S.div_tab_n, F[0] + X0*(F[S.div_tab_n - 1] - F[0]));
+                }
+            }
+            double fa = 1/sqrt(1 - so.x*so.x);
+            V3 sy = v3(0.0, -so.z*fa, so.y*fa);
+            V3 sx = cross3(so, sy);
+            double ct = cos(theta), stt = sin(theta), ca = cos(alpha), sa = sin(alpha);
+            s = v3(ct*so.x + stt*(ca*sx.x + sa*sy.x), ct*so.y + stt*(ca*sx.y + sa*sy.y), ct*so.z + stt*(ca*sx.z + sa*sy.z));
+        }
+        if (!(s.z > 0)) atomicOr(status, OTB_STATUS_NEG_DIR);
+
+        // ---- polarisation (ray_source.py:359-433)
+        if (!no_pol) {
+            double ang;
+            switch (S.polarization) {
+            case OTB_POL_CONSTANT: ang = S.pol_angle; break;
+            case OTB_POL_UNIFORM: ang = strat1(g, ST_POL, 0.0, 6.283185307179586); break;
+            case OTB_POL_LIST: {
+                const double* x = aux + S.pol_tab_off;
+                const double* F = x + S.pol_tab_n;
+                ang = x[icdf_next(F, S.pol_tab_n, strat1(g, ST_POL, 0.0, F[S.pol_tab_n - 1]))];
+                break;
+            }
+            default: {
+                const double* x = aux + S.pol_tab_off;
+                const double* F = x + S.pol_tab_n;
+                ang = icdf_linear(x, F, S.pol_tab_n, strat1(g, ST_POL, F[0], F[S.pol_tab_n - 1]));
+                ang = ang*0.017453292519943295;   // sic: the reference applies np.radians to the sampled angle (ray_source.py:392)
+                break;
+            }
+            }
+            V3 pol = v3(cos(ang), sin(ang), 0.0);
+            if (s.z != 1) {
+                double fa = 1/(sqrt(1 - s.z*s.z) + 1e-16);
+                V3 ps = v3(s.y*fa, -s.x*fa, 0.0);
+                double A_ts = ps.x*pol.x + ps.y*pol.y;
+                double A_tp = ps.y*pol.x - ps.x*pol.y;
+                V3 pp_ = cross3(ps, s);
+                pol = v3(ps.x*A_ts + pp_.x*A_tp, ps.y*A_ts + pp_.y*A_tp, ps.z*A_ts + pp_.z*A_tp);
+            }
+            pol0[k] = (float)pol.x;
+            pol0[k + N] = (float)pol.y;
+            pol0[k + 2*N] = (float)pol.z;
+        }
+
+        p0[k] = px;
+        p0[k + N] = py;
+        p0[k + 2*N] = pz;
+        s0[k] = s.x;
+        s0[k + N] = s.y;
+        s0[k + 2*N] = s.z;
+        w0[k] = (float)S.weight;
+        wl0[k] = (float)wl;
+    }
+}
+
+int otb_sm_count();
+
+extern "C" int otb_generate_rays(const OtbSource* sources_h, int n_sources, const double* gen_aux_d, int64_t N,
+                                 uint64_t seed, int64_t ray_offset, int no_pol, double* p0_d, double* s0_d,
+                                 float* pol0_d, float* w0_d, float* wl_d, void* stream)
+{
+    if (!sources_h || n_sources < 1 || !p0_d || !s0_d || !w0_d || !wl_d || (!no_pol && !pol0_d)) {
+        otb_set_error("null argument");
+        return OTB_ERR_INVALID_ARG;
+    }
+    if (N <= 0) return OTB_OK;
+    int64_t cover = 0;
+    for (int i = 0; i < n_sources; ++i) {
+        if (sources_h[i].ray_start != cover || sources_h[i].n_rays < 0) {
+            otb_set_error("sources must cover [0, N) with contiguous blocks (RayStorage.B_list)");
+            return OTB_ERR_INVALID_ARG;
+        }
+        cover += sources_h[i].n_rays;
+    }
+    if (cover != N) { otb_set_error("source ray counts do not sum to N"); return OTB_ERR_INVALID_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    OtbSource* src_d;
+    int* status_d;
+    OTB_CUDA(cudaMalloc(&src_d, sizeof(OtbSource)*n_sources));
+    OTB_CUDA(cudaMalloc(&status_d, sizeof(int)));
+    OTB_CUDA(cudaMemcpyAsync(src_d, sources_h, sizeof(OtbSource)*n_sources, cudaMemcpyHostToDevice, st));
+    OTB_CUDA(cudaMemsetAsync(status_d, 0, sizeof(int), st));
+    int64_t blocks = (N + 127)/128, cap = (int64_t)otb_sm_count()*16;
+    generate_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(src_d, n_sources, gen_aux_d, N, seed, ray_offset,
+                                                                              no_pol, p0_d, s0_d, pol0_d, w0_d, wl_d, status_d);
+    OTB_CUDA(cudaGetLastError());
+    int status = 0;
+    OTB_CUDA(cudaMemcpyAsync(&status, status_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OTB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(src_d);
+    cudaFree(status_d);
+    if (status & OTB_STATUS_NEG_DIR) {
+        otb_set_error("All ray divergences s need to be in positive z-divergence");
+        return OTB_ERR_GEOMETRY;
+    }
+    return OTB_OK;
+}

@@ -1,0 +1,263 @@
+// otb_render.cu — fused render mode: trace + detector test + XYZW binning with NO per-surface storage — the
+// per-chunk body of Raytracer.iterative_render (raytracer.py:1235-1264).
+//
+// The detector logic of Raytracer._hit_detector (raytracer.py:929-991) is evaluated online while the ray
+// segment i -> i+1 is still in registers: the walk starts at the section before the first stored point with
+// z >= z_min of the detector, a hit is valid unless it lies behind the next stored point (+C_EPS), and rays
+// whose points lie all behind or all before the detector's z-extent are ignored.  Segment directions are
+// recomputed from position differences exactly like RayStorage.rays_by_mask (ray_storage.py:273-285), so the
+// binned hits are identical to those of the store path.
+#include <string.h>
+#include "otb_step.cuh"
+#include "otb_bin.cuh"
+
+#define OTB_RENDER_THREADS 128
+#define OTB_MAX_DET 8
+
+struct RenderDet {
+    OtbDetector det;
+    BinGrid grid;
+    double* img;
+    int* cnt;
+    double* range;      // [4] hit range accumulation (mode 1)
+};
+
+struct RenderArgs {
+    DevScene sc;
+    OtbRays in;
+    const RenderDet* dets;
+    int n_det;
+    int mode;            // 0: bin into the images, 1: only accumulate the hit ranges (auto extent)
+    const double* obs;
+    unsigned long long* msgs;
+    int* status;
+    int nt;
+};
+
+struct DetState {
+    double X, Y;
+    float w;
+    bool started, finished, ok, all_start, all_noreach;
+};
+
+__device__ __forceinline__ void atomic_min_dd(double* addr, double v)
+{
+    unsigned long long* a = (unsigned long long*)addr;
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        if (!(v < __longlong_as_double((long long)assumed))) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (assumed != old);
+}
+__device__ __forceinline__ void atomic_max_dd(double* addr, double v)
+{
+    unsigned long long* a = (unsigned long long*)addr;
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        if (!(v > __longlong_as_double((long long)assumed))) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (assumed != old);
+}
+
+template <bool POL>
+__global__ void __launch_bounds__(OTB_RENDER_THREADS)
+trace_render_kernel(const RenderArgs a)
+{
+    extern __shared__ int smsgs[];
+    const DevScene& sc = a.sc;
+    const int nt = a.nt;
+    const int64_t N = a.in.N;
+    const int NDET = a.n_det;
+    for (int i = threadIdx.x; i < OTB_NMSG*nt; i += blockDim.x) smsgs[i] = 0;
+    __syncthreads();
+
+    for (int64_t base = (int64_t)blockIdx.x*blockDim.x; base < N; base += (int64_t)gridDim.x*blockDim.x) {
+        const int64_t ray = base + threadIdx.x;
+        const bool valid = ray < N;
+        RayState r;
+        if (valid) {
+            r.p = v3(a.in.p0_d[ray], a.in.p0_d[ray + N], a.in.p0_d[ray + 2*N]);
+            r.s = v3(a.in.s0_d[ray], a.in.s0_d[ray + N], a.in.s0_d[ray + 2*N]);
+            r.w = a.in.w0_d[ray];
+            r.wl = a.in.wl_d[ray];
+            if (POL) {
+                r.pol[0] = a.in.pol0_d[ray];
+                r.pol[1] = a.in.pol0_d[ray + N];
+                r.pol[2] = a.in.pol0_d[ray + 2*N];
+            }
+        } else {
+            r.p = v3(0, 0, 0);
+            r.s = v3(0, 0, 1);
+            r.w = 0.0f;
+            r.wl = 550.0f;
+            r.pol[0] = r.pol[1] = r.pol[2] = 0.0f;
+        }
+        r.n = medium_n(sc.media[sc.medium0], sc.aux, r.wl);
+        if (valid && r.n < 1.0) atomicOr(a.status, OTB_STATUS_NBELOW1);
+
+        DetState ds[OTB_MAX_DET];
+        for (int d = 0; d < NDET; ++d) {
+            const OtbSurface& D = a.dets[d].det.surface;
+            const bool bmin = r.p.z >= D.z_min, bmax = r.p.z >= D.z_max;
+            ds[d].X = ds[d].Y = 0.0;
+            ds[d].w = 0.0f;
+            ds[d].started = bmin;     // first stored point already at/behind z_min: the walk starts at section 0
+            ds[d].finished = false;
+            ds[d].ok = false;
+            ds[d].all_start = bmin && bmax;
+            ds[d].all_noreach = !bmin && !bmax;
+        }
+
+        for (int i = 0; i < sc.n_steps; ++i) {
+            const OtbStep& st = sc.steps[i];
+            double za = 0.0, zb = 0.0;
+            if (st.hurb && valid) {
+                if (a.in.hurb_z_d) {
+                    za = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 0)*N + ray];
+                    zb = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 1)*N + ray];
+                } else {
+                    Philox4 rnd = philox4x32_10((uint64_t)(a.in.ray_offset + ray), 0x48555242u, (uint32_t)st.hurb_slot, a.in.seed);
+                    normal2(rnd, za, zb);
+                }
+            }
+            const V3 p_i = r.p;
+            const float w_i = r.w;
+            StepFlags fl;
+            trace_step<POL>(sc, st, r, fl, za, zb, a.status);
+            book(smsgs, OTB_MSG_ILL_COND*nt + i + 1, valid && fl.ill);
+            book(smsgs, OTB_MSG_ABSORB_MISSING*nt + i + 1, valid && fl.absorb_missing);
+            book(smsgs, OTB_MSG_TIR*nt + i, valid && fl.tir);
+            book(smsgs, OTB_MSG_OUTLINE*nt + i, valid && fl.outline);
+            if (st.hurb) book(smsgs, OTB_MSG_HURB_NEG*nt + i + 1, valid && fl.hurb_neg);
+
+            // detector walk over section i = (p_i -> r.p)
+            for (int d = 0; d < NDET; ++d) {
+                const OtbSurface& D = a.dets[d].det.surface;
+                const bool bmin = r.p.z >= D.z_min, bmax = r.p.z >= D.z_max;
+                ds[d].all_start = ds[d].all_start && (bmin && bmax);
+                ds[d].all_noreach = ds[d].all_noreach && (!bmin && !bmax);
+                if (!ds[d].started && bmin) ds[d].started = true;     // section before the first point behind z_min
+                if (valid && ds[d].started && !ds[d].finished) {
+                    const V3 sd = unit3(v3(r.p.x - p_i.x, r.p.y - p_i.y, r.p.z - p_i.z));
+                    HitResult h = surf_find_hit(D, nullptr, p_i, sd, a.status);
+                    if (!(h.p.z > r.p.z + OTB_C_EPS)) {
+                        ds[d].finished = true;
+                        if (h.hit && w_i > 0.0f) {
+                            double X = h.p.x, Y = h.p.y;
+                            sphere_project(D, a.dets[d].det.projection, X, Y, h.p.z);
+                            ds[d].X = X;
+                            ds[d].Y = Y;
+                            ds[d].w = w_i;
+                            ds[d].ok = true;
+                        }
+                    }
+                }
+            }
+        }
+
+        // rays still walking at the last stored point have no further section: no hit (raytracer.py:970-978)
+        for (int d = 0; d < NDET; ++d) {
+            bool ok = valid && ds[d].ok && !(ds[d].all_start || ds[d].all_noreach);
+            const RenderDet& rd = a.dets[d];
+            if (ok && rd.det.has_extent) {
+                const double* e = rd.det.extent;
+                ok = (e[0] <= ds[d].X) && (ds[d].X <= e[1]) && (e[2] <= ds[d].Y) && (ds[d].Y <= e[3]);
+            }
+            if (a.mode == 0) {
+                if (ok) accumulate_hit(rd.grid, a.obs, ds[d].X, ds[d].Y, ds[d].w, r.wl, rd.img, rd.cnt);
+            } else {
+                double mnx = ok ? ds[d].X : INFINITY, mxx = ok ? ds[d].X : -INFINITY;
+                double mny = ok ? ds[d].Y : INFINITY, mxy = ok ? ds[d].Y : -INFINITY;
+#pragma unroll
+                for (int k = 16; k > 0; k >>= 1) {
+                    mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, k));
+                    mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, k));
+                    mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, k));
+                    mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, k));
+                }
+                if ((threadIdx.x & 31) == 0 && mnx <= mxx) {
+                    atomic_min_dd(&rd.range[0], mnx);
+                    atomic_max_dd(&rd.range[1], mxx);
+                    atomic_min_dd(&rd.range[2], mny);
+                    atomic_max_dd(&rd.range[3], mxy);
+                }
+            }
+        }
+    }
+
+    __syncthreads();
+    for (int i = threadIdx.x; i < OTB_NMSG*nt; i += blockDim.x)
+        if (smsgs[i]) atomicAdd(&a.msgs[i], (unsigned long long)smsgs[i]);
+}
+
+template <bool POL>
+static void launch_render(int blocks, size_t smem, cudaStream_t stream, const RenderArgs& a)
+{
+    trace_render_kernel<POL><<<blocks, OTB_RENDER_THREADS, smem, stream>>>(a);
+}
+
+int otb_observer_table(const double** out);
+BinGrid otb_make_grid(const double extent[4], int Nx, int Ny);
+int otb_sm_count();
+
+extern "C" int otb_trace_render(const OtbScene* scene, const OtbRays* rays, int n_det, const OtbDetector* dets_h,
+                                const double* extents_h, const int32_t* Nx_h, const int32_t* Ny_h,
+                                double* const* img_d, int32_t* const* cnt_d, double* range_d,
+                                int64_t* msgs_d, int32_t* status_d, void* stream)
+{
+    if (!scene || !rays || !dets_h || !msgs_d || !status_d) { otb_set_error("null argument"); return OTB_ERR_INVALID_ARG; }
+    if (n_det < 1 || n_det > OTB_MAX_DET) { otb_set_error("between 1 and %d detectors per fused launch", OTB_MAX_DET); return OTB_ERR_INVALID_ARG; }
+    const int mode = (img_d == nullptr) ? 1 : 0;
+    if (mode == 1 && !range_d) { otb_set_error("range_d required when no images are given"); return OTB_ERR_INVALID_ARG; }
+    if (mode == 0 && (!extents_h || !Nx_h || !Ny_h)) { otb_set_error("extents and grid sizes required"); return OTB_ERR_INVALID_ARG; }
+    if (rays->N <= 0) return OTB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    RenderDet hd[OTB_MAX_DET];
+    memset(hd, 0, sizeof(hd));
+    for (int d = 0; d < n_det; ++d) {
+        const int k = dets_h[d].surface.kind;
+        if (k == OTB_SURF_FUNC || k == OTB_SURF_DATA || k == OTB_SURF_ASPHERE) {
+            otb_set_error("Function/Data surfaces are not supported as detector surfaces (detector.py:37-41)");
+            return OTB_ERR_UNSUPPORTED;
+        }
+        hd[d].det = dets_h[d];
+        if (mode == 0) {
+            const double* e = extents_h + 4*d;
+            if (Nx_h[d] <= 0 || Ny_h[d] <= 0 || !(e[1] > e[0]) || !(e[3] > e[2]) || !img_d[d]) {
+                otb_set_error("invalid image grid for detector %d", d);
+                return OTB_ERR_INVALID_ARG;
+            }
+            hd[d].grid = otb_make_grid(e, Nx_h[d], Ny_h[d]);
+            hd[d].img = img_d[d];
+            hd[d].cnt = cnt_d ? cnt_d[d] : nullptr;
+        } else {
+            hd[d].range = range_d + 4*d;
+        }
+    }
+    RenderDet* dd;
+    OTB_CUDA(cudaMalloc(&dd, sizeof(RenderDet)*n_det));
+    OTB_CUDA(cudaMemcpyAsync(dd, hd, sizeof(RenderDet)*n_det, cudaMemcpyHostToDevice, st));
+    RenderArgs a;
+    a.sc = scene->dev;
+    a.in = *rays;
+    a.dets = dd;
+    a.n_det = n_det;
+    a.mode = mode;
+    if (int rc = otb_observer_table(&a.obs)) return rc;
+    a.msgs = (unsigned long long*)msgs_d;
+    a.status = status_d;
+    a.nt = scene->nt;
+    const int64_t N = rays->N;
+    int64_t blocks_needed = (N + OTB_RENDER_THREADS - 1)/OTB_RENDER_THREADS, cap = (int64_t)otb_sm_count()*16;
+    int blocks = (int)(blocks_needed < cap ? blocks_needed : cap);
+    size_t smem = sizeof(int)*OTB_NMSG*scene->nt;
+    if (scene->dev.no_pol) launch_render<false>(blocks, smem, st, a);
+    else launch_render<true>(blocks, smem, st, a);
+    cudaError_t e = cudaGetLastError();
+    OTB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dd);
+    if (e != cudaSuccess) return otb_cuda_fail(e, "trace_render_kernel launch");
+    return OTB_OK;
+}

@@ -1,0 +1,467 @@
+// otb_surfaces.cuh — per-ray surface primitives: mask, height, normal, intersection.
+// One thread = one ray; the surface record is warp-uniform, so the kind switches do not diverge.
+// References (relative to the reference repository): optrace/tracer/geometry/surface/*.py
+#pragma once
+#include "otb_common.cuh"
+
+struct HitResult {
+    V3 p;
+    bool hit;
+    bool ill;
+};
+
+// Surface._rotate_rc (surface.py:427-434) with host-precomputed cos/sin
+__device__ __forceinline__ void rot_rc(const OtbSurface& S, int cslot, double x, double y, double& xr, double& yr)
+{
+    if (S.flags & OTB_SF_ROTATED) {
+        double c = S.par[cslot], s = S.par[cslot + 1];
+        xr = x*c - y*s;
+        yr = x*s + y*c;
+    } else {
+        xr = x;
+        yr = y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// quartic B-splines (DataSurface: FITPACK knots/coefficients, data_surface_2d.py:76, 104)
+// ------------------------------------------------------------------------------------------------
+// index l with t[l] <= x < t[l+1], clamped to [k, n-k-2] (FITPACK splev / fpbisp interval search)
+__device__ __forceinline__ int bspl_interval(const double* __restrict__ t, int n, int k, double x)
+{
+    int lo = k, hi = n - k - 1;          // invariant: answer in [lo, hi-1]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (x >= t[mid]) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// de Boor–Cox recursion (FITPACK fpbspl): the deg+1 non-zero basis functions of degree `deg` at x
+template <int DEG>
+__device__ __forceinline__ void bspl_basis(const double* __restrict__ t, int l, double x, double* h)
+{
+    double hh[DEG + 1];
+    h[0] = 1.0;
+#pragma unroll
+    for (int j = 1; j <= DEG; ++j) {
+#pragma unroll
+        for (int i = 0; i < j; ++i) hh[i] = h[i];
+        h[0] = 0.0;
+#pragma unroll
+        for (int i = 0; i < j; ++i) {
+            int li = l + i + 1, lj = li - j;
+            double f = hh[i]/(t[li] - t[lj]);
+            h[i] = h[i] + f*(t[li] - x);
+            h[i + 1] = f*(x - t[lj]);
+        }
+    }
+}
+
+// 1-D spline value (nu = 0) or first derivative (nu = 1); extrapolates like splev(ext=0)
+__device__ inline double spline1d(const double* __restrict__ t, int n, const double* __restrict__ c, double x, int nu)
+{
+    int l = bspl_interval(t, n, 4, x);
+    if (nu == 0) {
+        double h[5];
+        bspl_basis<4>(t, l, x, h);
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) v += c[l - 4 + i]*h[i];
+        return v;
+    }
+    double h[4];
+    bspl_basis<3>(t, l, x, h);
+    double v = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int j = l - 3 + i;
+        double d = 4.0*(c[j] - c[j - 1])/(t[j + 4] - t[j]);
+        v += d*h[i];
+    }
+    return v;
+}
+
+// tensor-product spline value or partial derivative; arguments clamped to the knot domain like fpbisp
+__device__ inline double spline2d(const double* __restrict__ tx, int nx, const double* __restrict__ ty, int ny,
+                                  const double* __restrict__ c, double x, double y, int dx, int dy)
+{
+    x = fmin(fmax(x, tx[4]), tx[nx - 5]);
+    y = fmin(fmax(y, ty[4]), ty[ny - 5]);
+    int lx = bspl_interval(tx, nx, 4, x), ly = bspl_interval(ty, ny, 4, y);
+    int ncy = ny - 5;
+    double hx[5], hy[5];
+    if (!dx) bspl_basis<4>(tx, lx, x, hx); else bspl_basis<3>(tx, lx, x, hx);
+    if (!dy) bspl_basis<4>(ty, ly, y, hy); else bspl_basis<3>(ty, ly, y, hy);
+    double v = 0.0;
+    int nbx = dx ? 4 : 5, nby = dy ? 4 : 5;
+    for (int i = 0; i < nbx; ++i) {
+        int jx = dx ? (lx - 3 + i) : (lx - 4 + i);
+        double row = 0.0;
+        for (int j = 0; j < nby; ++j) {
+            int jy = dy ? (ly - 3 + j) : (ly - 4 + j);
+            double cc;
+            if (dx) cc = 4.0*(c[jx*ncy + jy] - c[(jx - 1)*ncy + jy])/(tx[jx + 4] - tx[jx]);
+            else if (dy) cc = 4.0*(c[jx*ncy + jy] - c[jx*ncy + jy - 1])/(ty[jy + 4] - ty[jy]);
+            else cc = c[jx*ncy + jy];
+            row += cc*hy[j];
+        }
+        v += row*hx[i];
+    }
+    return v;
+}
+
+// np.polyval (Horner), coefficients highest order first
+__device__ __forceinline__ double polyval(const double* __restrict__ c, int n, double x)
+{
+    double y = 0.0;
+    for (int i = 0; i < n; ++i) y = y*x + c[i];
+    return y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask: Surface.mask (surface.py:235-245), RingSurface.mask (ring_surface.py:123-133),
+// RectangularSurface.mask (rectangular_surface.py:100-112), SlitSurface.mask (slit_surface.py:89-102),
+// FunctionSurface2D.mask (function_surface_2d.py:158-191).  Absolute coordinates.
+// ------------------------------------------------------------------------------------------------
+__device__ inline bool surf_mask(const OtbSurface& S, double x, double y)
+{
+    const double x0 = S.pos[0], y0 = S.pos[1];
+    switch (S.kind) {
+    case OTB_SURF_RING: {
+        double dx = x - x0, dy = y - y0;
+        double r2 = dx*dx + dy*dy;
+        double a = S.par[OTB_P_RI] - OTB_N_EPS, b = S.r + OTB_N_EPS;
+        return (a*a <= r2) && (r2 <= b*b);
+    }
+    case OTB_SURF_RECT:
+    case OTB_SURF_SLIT: {
+        double xr, yr;
+        rot_rc(S, OTB_P_COSM, x - x0, y - y0, xr, yr);
+        double xe = S.par[OTB_P_DIMX]/2, ye = S.par[OTB_P_DIMY]/2;
+        bool m = (-xe - OTB_N_EPS <= xr) && (xr <= xe + OTB_N_EPS) && (-ye - OTB_N_EPS <= yr) && (yr <= ye + OTB_N_EPS);
+        if (S.kind == OTB_SURF_SLIT) {
+            double xi = S.par[OTB_P_DIMIX]/2, yi = S.par[OTB_P_DIMIY]/2;
+            bool inside = (-xi + OTB_N_EPS <= xr) && (xr <= xi - OTB_N_EPS) && (-yi + OTB_N_EPS <= yr) && (yr <= yi - OTB_N_EPS);
+            m = m && !inside;
+        }
+        return m;
+    }
+    default: {
+        double dx = x - x0, dy = y - y0;
+        double b = S.r + OTB_N_EPS;
+        bool m = dx*dx + dy*dy <= b*b;
+        if (S.kind == OTB_SURF_FUNC && (S.flags & OTB_SF_HAS_MASK)) {
+            int id = (int)S.par[OTB_P_FMASK];
+            double mf;
+            if (S.flags & OTB_SF_1D) {
+                mf = otb_user_f1(id, sqrt(dx*dx + dy*dy));
+            } else {
+                double xr, yr;
+                rot_rc(S, OTB_P_COSM, dx, dy, xr, yr);
+                mf = otb_user_f2(id, xr, S.par[OTB_P_SIGN]*yr);
+            }
+            m = m && (mf != 0.0);
+        }
+        return m;
+    }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// relative height without masking: Surface._values and overrides
+// (conic_surface.py:57-68, tilted_surface.py:61-74, aspheric_surface.py:51-66,
+//  function_surface_2d.py:133-156, data_surface_2d.py:130-153)
+// ------------------------------------------------------------------------------------------------
+__device__ inline double surf_values_rel(const OtbSurface& S, const double* __restrict__ aux, double x, double y)
+{
+    switch (S.kind) {
+    case OTB_SURF_CONIC: {
+        double r2 = x*x + y*y;
+        return S.par[OTB_P_RHO]*r2/(1 + sqrt(1 - S.par[OTB_P_KP1RHO2]*r2));
+    }
+    case OTB_SURF_TILTED:
+        return x*S.par[OTB_P_MX] + y*S.par[OTB_P_MY];
+    case OTB_SURF_ASPHERE: {
+        double r = sqrt(x*x + y*y);
+        double r2 = r*r;
+        double z = S.par[OTB_P_RHO]*r2/(1 + sqrt(1 - S.par[OTB_P_KP1RHO2]*r2));
+        z = z + polyval(aux + S.aux_off, S.aux_n0, r);
+        return z - S.par[OTB_P_R];
+    }
+    case OTB_SURF_FUNC: {
+        double sign = S.par[OTB_P_SIGN], v;
+        if (S.flags & OTB_SF_1D) {
+            v = otb_user_f1(S.func_id, sqrt(x*x + y*y));
+        } else {
+            double xr, yr;
+            rot_rc(S, OTB_P_COSM, x, y, xr, yr);
+            v = otb_user_f2(S.func_id, xr, sign*yr);
+        }
+        return sign*(v - S.par[OTB_P_OFFSET]);
+    }
+    case OTB_SURF_DATA: {
+        double sign = S.par[OTB_P_SIGN], v;
+        const double* t = aux + S.aux_off;
+        if (S.flags & OTB_SF_1D) {
+            v = spline1d(t, S.aux_n0, t + S.aux_n0, hypot(x, sign*y), 0);
+        } else {
+            double xr, yr;
+            rot_rc(S, OTB_P_COSM, x, y, xr, yr);
+            v = spline2d(t, S.aux_n0, t + S.aux_n0, S.aux_n1, t + S.aux_n0 + S.aux_n1, xr, sign*yr, 0, 0);
+        }
+        return sign*(v - S.par[OTB_P_OFFSET]);
+    }
+    default:
+        return 0.0;
+    }
+}
+
+// Surface.values (surface.py:137-164): absolute height with the radially continued edge
+__device__ inline double surf_values(const OtbSurface& S, const double* __restrict__ aux, double x, double y)
+{
+    if (S.flags & OTB_SF_FLAT) return S.z_max;
+    if (surf_mask(S, x, y)) return S.pos[2] + surf_values_rel(S, aux, x - S.pos[0], y - S.pos[1]);
+    if (S.flags & OTB_SF_ROTSYM) return S.pos[2] + S.par[OTB_P_EDGEZ];
+    double r = S.r - OTB_N_EPS;
+    double phi = atan2(y - S.pos[1], x - S.pos[0]);
+    return S.pos[2] + surf_values_rel(S, aux, r*cos(phi), r*sin(phi));
+}
+
+// ------------------------------------------------------------------------------------------------
+// normals: Surface.normals (surface.py:247-285), ConicSurface.normals (conic_surface.py:70-124),
+// TiltedSurface.normals (tilted_surface.py:76-89), FunctionSurface2D.normals
+// (function_surface_2d.py:193-253), DataSurface2D.normals (data_surface_2d.py:155-196)
+// ------------------------------------------------------------------------------------------------
+__device__ inline V3 surf_normal(const OtbSurface& S, const double* __restrict__ aux, double x, double y)
+{
+    const int k = S.kind;
+    if ((S.flags & OTB_SF_FLAT) && k != OTB_SURF_TILTED) return v3(0.0, 0.0, 1.0);
+    if (!surf_mask(S, x, y)) return v3(0.0, 0.0, 1.0);
+    const double x0 = S.pos[0], y0 = S.pos[1];
+    const double dx = x - x0, dy = y - y0;
+
+    if (k == OTB_SURF_CONIC) {
+        double rho = S.par[OTB_P_RHO];
+        if (S.par[OTB_P_K] == 0.0) {
+            double rho2 = S.par[OTB_P_RHO2];
+            return v3(-rho*dx, -rho*dy, sqrt(1 - rho2*(dx*dx) - rho2*(dy*dy)));
+        }
+        double r = sqrt(dx*dx + dy*dy);
+        double phi = atan2(dy, dx);
+        double n_r = -rho*r/sqrt(1 - S.par[OTB_P_KRHO2]*(r*r));
+        return v3(n_r*cos(phi), n_r*sin(phi), sqrt(1 - n_r*n_r));
+    }
+    if (k == OTB_SURF_TILTED) return v3(S.par[OTB_P_NX], S.par[OTB_P_NY], S.par[OTB_P_NZ]);
+
+    const bool analytic = (k == OTB_SURF_ASPHERE) || (k == OTB_SURF_DATA) || (k == OTB_SURF_FUNC && (S.flags & OTB_SF_HAS_DERIV));
+    if (analytic) {
+        double nxn, nyn;
+        if (S.flags & OTB_SF_1D) {
+            double phi = atan2(dy, dx), nr;
+            if (k == OTB_SURF_ASPHERE) {
+                double rm = sqrt(dx*dx + dy*dy);
+                double fr = rm*S.par[OTB_P_RHO]/sqrt(1 - S.par[OTB_P_KP1RHO2]*(rm*rm));
+                nr = fr + polyval(aux + S.aux_off + S.aux_n0, S.aux_n1, rm);
+            } else if (k == OTB_SURF_FUNC) {
+                nr = S.par[OTB_P_SIGN]*otb_user_f1((int)S.par[OTB_P_FDERIV], sqrt(dx*dx + dy*dy));
+            } else {
+                const double* t = aux + S.aux_off;
+                nr = S.par[OTB_P_SIGN]*spline1d(t, S.aux_n0, t + S.aux_n0, hypot(dx, dy), 1);
+            }
+            nxn = nr*cos(phi);
+            nyn = nr*sin(phi);
+        } else {
+            double sign = S.par[OTB_P_SIGN], a, b;
+            if (k == OTB_SURF_FUNC) {
+                otb_user_d2((int)S.par[OTB_P_FDERIV], dx, sign*dy, &a, &b);   // unrotated, function_surface_2d.py:234
+                a = a*sign;
+            } else {
+                double xr, yr;
+                rot_rc(S, OTB_P_COSM, dx, dy, xr, yr);
+                const double* t = aux + S.aux_off;
+                const double *ty = t + S.aux_n0, *c = t + S.aux_n0 + S.aux_n1;
+                a = spline2d(t, S.aux_n0, ty, S.aux_n1, c, xr, sign*yr, 1, 0)*sign;
+                b = spline2d(t, S.aux_n0, ty, S.aux_n1, c, xr, sign*yr, 0, 1);
+            }
+            rot_rc(S, OTB_P_COSP, a, b, nxn, nyn);
+        }
+        return unit3(v3(-nxn, -nyn, 1.0));
+    }
+
+    // central differences (surface.py:266-283)
+    double eps = S.par[OTB_P_FDEPS];
+    V3 n;
+    n.x = surf_values_rel(S, aux, dx - eps, dy) - surf_values_rel(S, aux, dx + eps, dy);
+    n.y = surf_values_rel(S, aux, dx, dy - eps) - surf_values_rel(S, aux, dx, dy + eps);
+    n.z = 2*eps;
+    return unit3(n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// intersection
+// ------------------------------------------------------------------------------------------------
+// Surface._find_hit_handle_abnormal (surface.py:436-479)
+__device__ inline void handle_abnormal(const OtbSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, HitResult& h)
+{
+    double zs = surf_values(S, aux, h.p.x, h.p.y);
+    bool dev = fabs(h.p.z - zs) > OTB_C_EPS;
+    bool beh = p.z > S.z_max + OTB_N_EPS;
+    bool neg = h.p.z < p.z - OTB_C_EPS;
+    bool bet = (neg || dev) && !beh;
+    if (bet) {
+        double tnm = (S.z_max - p.z)/s.z;
+        h.p = along(p, s, tnm);
+        h.hit = false;
+    }
+    if (beh) {
+        h.p = p;
+        h.hit = false;
+    }
+}
+
+// Surface.find_hit (surface.py:307-414): plane for flat surfaces, Illinois regula falsi otherwise.
+// `status` receives OTB_STATUS_TIMEOUT when the 200-iteration limit is reached (surface.py:403).
+__device__ inline HitResult find_hit_numeric(const OtbSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
+{
+    HitResult h;
+    h.ill = false;
+    if (S.flags & OTB_SF_FLAT) {
+        double t = (S.pos[2] - p.z)/s.z;
+        h.p = along(p, s, t);
+        h.hit = surf_mask(S, h.p.x, h.p.y);
+        handle_abnormal(S, aux, p, s, h);
+        return h;
+    }
+    double t1 = (S.z_min - OTB_C_EPS/10 - p.z)/s.z;
+    double t2 = (S.z_max + OTB_C_EPS/10 - p.z)/s.z;
+    if (t1 < 0) t1 = -OTB_C_EPS;
+    V3 p1 = along(p, s, t1), p2 = along(p, s, t2);
+    double f1 = p1.z - surf_values(S, aux, p1.x, p1.y);
+    double f2 = p2.z - surf_values(S, aux, p2.x, p2.y);
+    bool w = true;
+    if (!finite_d(t1) || !finite_d(t2)) w = false;
+    if ((t2 - t1) < OTB_C_EPS) w = false;
+    h.p = w ? v3(0.0, 0.0, 0.0) : p1;
+    h.ill = f1*f2 > 0;
+    int it = 1;
+    while (w) {
+        double ts = t1 - f1/(f2 - f1)*(t2 - t1);
+        V3 pl = along(p, s, ts);
+        double fts = pl.z - surf_values(S, aux, pl.x, pl.y);
+        double prod = fts*f2;
+        if (prod < 0) {            // case 1: [t2, ts]
+            t1 = t2; t2 = ts; f1 = f2; f2 = fts;
+        } else if (prod > 0) {     // case 2: [t1, ts], Illinois factor 0.5 on the retained end
+            t2 = ts; f1 = 0.5*f1; f2 = fts;
+        } else if (prod == 0) {    // case 3: exact root
+            t1 = ts; t2 = ts; f1 = fts; f2 = fts;
+        }
+        if (fabs(t2 - t1) < OTB_C_EPS/10) {
+            h.p = pl;
+            w = false;
+        } else if (it == 200) {
+            atomicOr(status, OTB_STATUS_TIMEOUT);
+            h.p = pl;
+            w = false;
+        }
+        ++it;
+    }
+    h.hit = surf_mask(S, h.p.x, h.p.y);
+    handle_abnormal(S, aux, p, s, h);
+    return h;
+}
+
+// ConicSurface.find_hit (conic_surface.py:126-203)
+__device__ inline HitResult find_hit_conic(const OtbSurface& S, const V3& p, const V3& s)
+{
+    HitResult h;
+    h.ill = false;
+    const double ox = p.x - S.pos[0], oy = p.y - S.pos[1], oz = p.z - S.pos[2];
+    const double k = S.par[OTB_P_K], kp1 = S.par[OTB_P_KP1];
+    const double A = (k != 0.0) ? 1 + k*(s.z*s.z) : 1.0;
+    const double B = s.x*ox + s.y*oy + s.z*(oz*kp1 - S.par[OTB_P_INVRHO]);
+    const double Cc = oy*oy + ox*ox + oz*(oz*kp1 - S.par[OTB_P_TWOINVRHO]);
+    const double D = sqrt(B*B - Cc*A);
+    const double t1 = (-B - D)/A, t2 = (-B + D)/A;
+    const double z = p.z;
+    const double z1 = z + s.z*t1, z2 = z + s.z*t2;
+    const double z_min = S.z_min - OTB_N_EPS, z_max = S.z_max + OTB_N_EPS;
+    const bool c1 = (z_min <= z1) && (z1 <= z_max) && (z1 >= z);
+    const bool c2 = (z_min <= z2) && (z2 <= z_max) && (z2 >= z) && (t2 < t1);
+    double t = (c1 && !c2) ? t1 : t2;
+    h.p = along(p, s, t);
+    h.hit = surf_mask(S, h.p.x, h.p.y);
+    if (A == 0.0 && B != 0.0) {
+        double tl = -Cc/(2*B);
+        h.p = along(p, s, tl);
+        h.hit = surf_mask(S, h.p.x, h.p.y);
+    }
+    bool nh = !h.hit || !finite_d(D) || (A == 0.0 && B == 0.0) || (h.p.z < z_min) || (h.p.z > z_max);
+    if (nh) {
+        double tnh = (S.z_max - p.z)/s.z;
+        h.p = along(p, s, tnh);
+        h.hit = false;
+    }
+    if (z > S.z_max) {
+        h.p = p;
+        h.hit = false;
+    }
+    return h;
+}
+
+// TiltedSurface.find_hit (tilted_surface.py:91-123)
+__device__ inline HitResult find_hit_tilted(const OtbSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
+{
+    HitResult h;
+    const V3 n = v3(S.par[OTB_P_NX], S.par[OTB_P_NY], S.par[OTB_P_NZ]);
+    double t_denom = dot3(s, n);
+    bool nz = t_denom != 0;
+    V3 d = v3(S.pos[0] - p.x, S.pos[1] - p.y, S.pos[2] - p.z);
+    double t = dot3(d, n)/(nz ? t_denom : 1e-12);
+    h.p = along(p, s, t);
+    h.hit = surf_mask(S, h.p.x, h.p.y) && nz;
+    h.ill = false;
+    if (!h.hit) h = find_hit_numeric(S, aux, p, s, status);
+    handle_abnormal(S, aux, p, s, h);
+    return h;
+}
+
+__device__ inline HitResult surf_find_hit(const OtbSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
+{
+    switch (S.kind) {
+    case OTB_SURF_CONIC: return find_hit_conic(S, p, s);
+    case OTB_SURF_TILTED: return find_hit_tilted(S, aux, p, s, status);
+    default: return find_hit_numeric(S, aux, p, s, status);
+    }
+}
+
+// SphericalSurface.sphere_projection (spherical_surface.py:36-97), in place on (x, y) given z
+__device__ __forceinline__ void sphere_project(const OtbSurface& S, int method, double& x, double& y, double z)
+{
+    if (method == OTB_PROJ_NONE || method == OTB_PROJ_ORTHOGRAPHIC) return;
+    const double R = S.par[OTB_P_R];
+    const double dx = x - S.pos[0], dy = y - S.pos[1];
+    const double zm = S.pos[2] + R;
+    const double sgn = (R > 0) ? 1.0 : ((R < 0) ? -1.0 : 0.0);
+    if (method == OTB_PROJ_EQUIDISTANT) {
+        double r = sqrt(dx*dx + dy*dy);
+        double theta = -sgn*atan(r/(z - zm));
+        double phi = atan2(dy, dx);
+        x = theta*cos(phi);
+        y = theta*sin(phi);
+    } else if (method == OTB_PROJ_STEREOGRAPHIC) {
+        double r = sqrt(dx*dx + dy*dy);
+        double theta = 1.5707963267948966 - atan(r/(z - zm));
+        double phi = atan2(dy, dx);
+        double rr = -2*sgn*tan(0.7853981633974483 - theta/2);
+        x = rr*cos(phi);
+        y = rr*sin(phi);
+    } else {   // Equal-Area
+        double x_ = dx/fabs(R), y_ = dy/fabs(R), z_ = (z - zm)/R;
+        double f = sqrt(2/(1 - z_));
+        x = f*x_;
+        y = f*y_;
+    }
+}
+

@@ -1,0 +1,146 @@
+// otb_trace.cu — store-mode trace kernel: the whole surface loop of Raytracer.trace (raytracer.py:297-397)
+// in ONE launch.  Thread = ray, ray state in registers, every section written once as coalesced SoA planes
+// in the byte layout of RayStorage (ray_storage.py:80-90).  No tensor cores: the path is not a contraction.
+//
+// HBM traffic per ray: read 68 B (injected bundle) ; write nt*48 + 24 B (pol) or nt*36 + 24 B (no_pol).
+#include "otb_step.cuh"
+
+#define OTB_TRACE_THREADS 128
+
+struct TraceArgs {
+    DevScene sc;
+    OtbRays in;
+    OtbRayStore out;
+    unsigned long long* msgs;   // [OTB_NMSG * nt]
+    int* status;
+};
+
+
+template <bool POL>
+__global__ void __launch_bounds__(OTB_TRACE_THREADS)
+trace_store_kernel(const TraceArgs a)
+{
+    extern __shared__ int smsgs[];      // [OTB_NMSG * nt]
+    const DevScene& sc = a.sc;
+    const int nt = a.out.nt;
+    const int64_t N = a.out.N;
+    for (int i = threadIdx.x; i < OTB_NMSG*nt; i += blockDim.x) smsgs[i] = 0;
+    __syncthreads();
+
+    double* __restrict__ P = a.out.p_d;
+    float* __restrict__ Wt = a.out.w_d;
+    float* __restrict__ PL = a.out.pol_d;
+    double* __restrict__ NS = a.out.n_d;
+    const int64_t Nnt = N*(int64_t)nt;
+
+    for (int64_t base = (int64_t)blockIdx.x*blockDim.x; base < N; base += (int64_t)gridDim.x*blockDim.x) {
+        const int64_t ray = base + threadIdx.x;
+        const bool valid = ray < N;
+        RayState r;
+        if (valid) {
+            r.p = v3(a.in.p0_d[ray], a.in.p0_d[ray + N], a.in.p0_d[ray + 2*N]);
+            r.s = v3(a.in.s0_d[ray], a.in.s0_d[ray + N], a.in.s0_d[ray + 2*N]);
+            r.w = a.in.w0_d[ray];
+            r.wl = a.in.wl_d[ray];
+            if (POL) {
+                r.pol[0] = a.in.pol0_d[ray];
+                r.pol[1] = a.in.pol0_d[ray + N];
+                r.pol[2] = a.in.pol0_d[ray + 2*N];
+            }
+        } else {
+            r.p = v3(0, 0, 0);
+            r.s = v3(0, 0, 1);
+            r.w = 0.0f;
+            r.wl = 550.0f;
+            r.pol[0] = r.pol[1] = r.pol[2] = 0.0f;
+        }
+        r.n = medium_n(sc.media[sc.medium0], sc.aux, r.wl);
+        if (valid && r.n < 1.0) atomicOr(a.status, OTB_STATUS_NBELOW1);
+
+        if (valid) {
+            __stcs(&P[ray], r.p.x);
+            __stcs(&P[ray + Nnt], r.p.y);
+            __stcs(&P[ray + 2*Nnt], r.p.z);
+            __stcs(&Wt[ray], r.w);
+            __stcs(&NS[ray], r.n);
+            __stcs(&a.out.wl_d[ray], r.wl);
+            if (POL) {
+                __stcs(&PL[ray], r.pol[0]);
+                __stcs(&PL[ray + Nnt], r.pol[1]);
+                __stcs(&PL[ray + 2*Nnt], r.pol[2]);
+            }
+        }
+
+        for (int i = 0; i < sc.n_steps; ++i) {
+            const OtbStep& st = sc.steps[i];
+            double za = 0.0, zb = 0.0;
+            if (st.hurb && valid) {
+                if (a.in.hurb_z_d) {
+                    za = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 0)*N + ray];
+                    zb = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 1)*N + ray];
+                } else {
+                    Philox4 rnd = philox4x32_10((uint64_t)(a.in.ray_offset + ray), 0x48555242u, (uint32_t)st.hurb_slot, a.in.seed);
+                    normal2(rnd, za, zb);
+                }
+            }
+            StepFlags fl;
+            trace_step<POL>(sc, st, r, fl, za, zb, a.status);
+
+            // message booking (section indices as in raytracer.py:318, 323, 486 vs :718, 826)
+            book(smsgs, OTB_MSG_ILL_COND*nt + i + 1, valid && fl.ill);
+            book(smsgs, OTB_MSG_ABSORB_MISSING*nt + i + 1, valid && fl.absorb_missing);
+            book(smsgs, OTB_MSG_TIR*nt + i, valid && fl.tir);
+            book(smsgs, OTB_MSG_OUTLINE*nt + i, valid && fl.outline);
+            if (st.hurb) book(smsgs, OTB_MSG_HURB_NEG*nt + i + 1, valid && fl.hurb_neg);
+
+            if (valid) {
+                const int64_t o = ray + N*(int64_t)(i + 1);
+                __stcs(&P[o], r.p.x);
+                __stcs(&P[o + Nnt], r.p.y);
+                __stcs(&P[o + 2*Nnt], r.p.z);
+                __stcs(&Wt[o], r.w);
+                __stcs(&NS[o], r.n);
+                if (POL) {
+                    __stcs(&PL[o], r.pol[0]);
+                    __stcs(&PL[o + Nnt], r.pol[1]);
+                    __stcs(&PL[o + 2*Nnt], r.pol[2]);
+                }
+            }
+        }
+        if (valid) {
+            __stcs(&a.out.s_d[ray], r.s.x);
+            __stcs(&a.out.s_d[ray + N], r.s.y);
+            __stcs(&a.out.s_d[ray + 2*N], r.s.z);
+        }
+    }
+
+    __syncthreads();
+    for (int i = threadIdx.x; i < OTB_NMSG*nt; i += blockDim.x)
+        if (smsgs[i]) atomicAdd(&a.msgs[i], (unsigned long long)smsgs[i]);
+}
+
+int otb_launch_trace_store(const OtbScene* scene, const OtbRays* rays, const OtbRayStore* out,
+                           int64_t* msgs_d, int32_t* status_d, cudaStream_t stream, int sm_count)
+{
+    TraceArgs a;
+    a.sc = scene->dev;
+    a.in = *rays;
+    a.out = *out;
+    a.msgs = (unsigned long long*)msgs_d;
+    a.status = status_d;
+    const int64_t N = out->N;
+    if (N <= 0) return OTB_OK;
+    const int threads = OTB_TRACE_THREADS;
+    int64_t blocks_needed = (N + threads - 1)/threads;
+    // persistent-style grid: a multiple of the SM count, grid-stride over rays
+    int64_t cap = (int64_t)sm_count*16;
+    int blocks = (int)(blocks_needed < cap ? blocks_needed : cap);
+    size_t smem = sizeof(int)*OTB_NMSG*out->nt;
+    if (scene->dev.no_pol)
+        trace_store_kernel<false><<<blocks, threads, smem, stream>>>(a);
+    else
+        trace_store_kernel<true><<<blocks, threads, smem, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return otb_cuda_fail(e, "trace_store_kernel launch");
+    return OTB_OK;
+}

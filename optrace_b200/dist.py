@@ -1,0 +1,90 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), rays sharded by contiguous global ray-id ranges,
+no collective on the propagation path.  Only detector histograms, hit-extent bounds, message counters and
+flux statistics are reduced (NCCL all-reduce over NVLink on GPU tensors; gloo on CPU tensors in the tests).
+
+The reference has no distributed backend at all; its analogue is the per-thread ray ranges of
+raytracer.py:285-286, 399-405.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _td():
+    import torch.distributed as td
+    return td
+
+
+def is_dist() -> bool:
+    td = _td()
+    return td.is_available() and td.is_initialized()
+
+
+def world() -> int:
+    return _td().get_world_size() if is_dist() else 1
+
+
+def rank() -> int:
+    return _td().get_rank() if is_dist() else 0
+
+
+def shard_range(N: int, r: int | None = None, G: int | None = None) -> tuple[int, int]:
+    """contiguous global ray-id range [begin, end) of rank r among G ranks; the last rank takes the remainder
+    (same rule as RayStorage.thread_rays, ray_storage.py:146-148)"""
+    r = rank() if r is None else r
+    G = world() if G is None else G
+    Np = int(N/G)
+    begin = r*Np
+    end = begin + Np if r != G - 1 else N
+    return begin, end
+
+
+def source_slices(B_list, begin: int, end: int) -> list[tuple[int, int, int]]:
+    """(source index, local start, count) of every source block intersecting [begin, end)
+    (the per-thread source walk of ray_storage.py:150-168)"""
+    out = []
+    for i in range(len(B_list) - 1):
+        s, e = max(begin, int(B_list[i])), min(int(B_list[i + 1]), end)
+        if e > s:
+            out.append((i, s - begin, e - s))
+    return out
+
+
+def allreduce_sum_(t):
+    """in-place SUM all-reduce (histograms, counters)"""
+    if is_dist() and world() > 1:
+        td = _td()
+        td.all_reduce(t, op=td.ReduceOp.SUM)
+    return t
+
+
+def allreduce_range_(rng):
+    """rng = [min x, max x, min y, max y] tensor: MIN/MAX all-reduce for the auto extent (raytracer.py:1042-1046)"""
+    if is_dist() and world() > 1:
+        td = _td()
+        sign = rng.new_tensor([-1.0, 1.0, -1.0, 1.0])
+        v = rng*sign                    # turn the minima into maxima
+        td.all_reduce(v, op=td.ReduceOp.MAX)
+        rng.copy_(v*sign)
+    return rng
+
+
+def allreduce_max_scalar(v: float, device) -> float:
+    if is_dist() and world() > 1:
+        import torch
+        td = _td()
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+    return v
+
+
+def broadcast_ints(a: np.ndarray, device) -> np.ndarray:
+    """rank 0's integer array to all ranks (per-source ray counts involve np.random.choice, ray_storage.py:63-68)"""
+    if is_dist() and world() > 1:
+        import torch
+        td = _td()
+        t = torch.as_tensor(np.asarray(a, dtype=np.int64), device=device)
+        td.broadcast(t, src=0)
+        return t.cpu().numpy()
+    return np.asarray(a, dtype=np.int64)

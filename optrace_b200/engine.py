@@ -1,0 +1,319 @@
+"""Thin Python front of the CUDA engine: torch provides device memory, streams and (elsewhere)
+torch.distributed; every computation is a call through the C ABI of include/otb.h (ctypes, _cabi.py).
+
+There is no CPU fallback here: without a CUDA device `ensure_init()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import check
+
+_initialised = None
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def ensure_init():
+    """Loads libotb.so and binds it to the current CUDA device (torch.cuda.current_device())."""
+    global _initialised
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise _cabi.EngineError("No CUDA device available: the optrace_b200 engine runs on B200 GPUs only "
+                                "(there is no CPU fallback).")
+    dev = torch.cuda.current_device()
+    if _initialised != dev:
+        l = _cabi.lib()
+        check(l.otb_init(dev), l)
+        _initialised = dev
+    return _cabi.lib()
+
+
+def stream_ptr():
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def device():
+    torch = _torch()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def dptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def to_dev(a: np.ndarray, dtype=None):
+    """host array -> flat device tensor in Fortran (plane) order"""
+    torch = _torch()
+    a = np.asarray(a, dtype=dtype)
+    flat = np.ascontiguousarray(a.reshape(-1, order="F"))
+    return torch.from_numpy(flat).to(device(), non_blocking=False)
+
+
+# ---------------------------------------------------------------------------------------------------
+# scene handle
+# ---------------------------------------------------------------------------------------------------
+class SceneHandle:
+    """Device-resident copy of a FlatScene (otb_scene_create / otb_scene_destroy)."""
+
+    def __init__(self, flat):
+        self.lib = ensure_init() if not flat.user_funcs else _user_lib(flat)
+        self.flat = flat
+        desc = flat.to_ctypes()
+        h = C.c_void_p()
+        check(self.lib.otb_scene_create(C.byref(desc), C.byref(h)), self.lib)
+        self.handle = h
+        self.nt = flat.nt
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.otb_scene_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _user_lib(flat):
+    """engine build specialised with the scene's user callables (userfunc.py)"""
+    from . import userfunc
+    ensure_init()
+    path = userfunc.build_specialised_library(flat.user_funcs)
+    l = _cabi.lib(path)
+    check(l.otb_init(_torch().cuda.current_device()), l)
+    return l
+
+
+# ---------------------------------------------------------------------------------------------------
+# trace
+# ---------------------------------------------------------------------------------------------------
+class DeviceRays:
+    """initial bundle on the device (SoA planes)"""
+
+    def __init__(self, N, p0, s0, pol0, w0, wl, hurb_z=None, seed=0, ray_offset=0):
+        self.N, self.p0, self.s0, self.pol0, self.w0, self.wl = N, p0, s0, pol0, w0, wl
+        self.hurb_z, self.seed, self.ray_offset = hurb_z, seed, ray_offset
+
+    @staticmethod
+    def from_host(p, s, pol, w, wl, hurb_z=None, seed=0):
+        N = p.shape[0]
+        return DeviceRays(N, to_dev(p, np.float64), to_dev(s, np.float64),
+                          None if pol is None else to_dev(pol, np.float32),
+                          to_dev(w, np.float32), to_dev(wl, np.float32),
+                          None if hurb_z is None else _torch().from_numpy(
+                              np.ascontiguousarray(hurb_z, dtype=np.float64).ravel()).to(device()), seed)
+
+    def c_struct(self):
+        r = _cabi.OtbRays()
+        r.N = self.N
+        r.p0_d, r.s0_d, r.pol0_d = dptr(self.p0), dptr(self.s0), dptr(self.pol0)
+        r.w0_d, r.wl_d, r.hurb_z_d = dptr(self.w0), dptr(self.wl), dptr(self.hurb_z)
+        r.seed, r.ray_offset = self.seed, self.ray_offset
+        return r
+
+
+class DeviceStore:
+    """per-surface ray storage on the device, byte layout of RayStorage (ray_storage.py:80-90)"""
+
+    def __init__(self, N: int, nt: int, no_pol: bool):
+        torch = _torch()
+        d = device()
+        self.N, self.nt, self.no_pol = N, nt, no_pol
+        self.p = torch.empty(N*nt*3, dtype=torch.float64, device=d)
+        self.s = torch.empty(N*3, dtype=torch.float64, device=d)
+        self.w = torch.empty(N*nt, dtype=torch.float32, device=d)
+        self.n = torch.empty(N*nt, dtype=torch.float64, device=d)
+        self.wl = torch.empty(N, dtype=torch.float32, device=d)
+        self.pol = None if no_pol else torch.empty(N*nt*3, dtype=torch.float32, device=d)
+
+    def c_struct(self):
+        s = _cabi.OtbRayStore()
+        s.N, s.nt = self.N, self.nt
+        s.p_d, s.s_d, s.pol_d = dptr(self.p), dptr(self.s), dptr(self.pol)
+        s.w_d, s.n_d, s.wl_d = dptr(self.w), dptr(self.n), dptr(self.wl)
+        return s
+
+    @staticmethod
+    def nbytes(N: int, nt: int, no_pol: bool) -> int:
+        """RayStorage.storage_size (ray_storage.py:92-104)"""
+        fpol = 4*N*nt*3 if not no_pol else 8
+        return N*nt*3*8 + N*3*8 + fpol + N*nt*4 + N*nt*8 + N*4
+
+
+def trace_store(scene: SceneHandle, rays: DeviceRays, store: DeviceStore | None = None, msgs=None, sync=True):
+    """otb_trace_store: returns (store, msgs int64 tensor (5, nt) on device, status tensor)"""
+    torch = _torch()
+    if store is None:
+        store = DeviceStore(rays.N, scene.nt, scene.flat.no_pol)
+    if msgs is None:
+        msgs = torch.zeros(_cabi.NMSG*scene.nt, dtype=torch.int64, device=device())
+    status = torch.zeros(1, dtype=torch.int32, device=device())
+    r, s = rays.c_struct(), store.c_struct()
+    check(scene.lib.otb_trace_store(scene.handle, C.byref(r), C.byref(s), dptr(msgs), dptr(status), stream_ptr()),
+          scene.lib)
+    if sync:
+        raise_status(int(status.item()))
+    return store, msgs.view(_cabi.NMSG, scene.nt), status
+
+
+def raise_status(st: int):
+    if st & 1:
+        raise TimeoutError("Timeout after 200 iterations in hit finding. Try retracing.")
+    if st & 2:
+        raise RuntimeError("Refraction index below 1 for a traced wavelength.")
+    if st & 4:
+        raise _cabi.EngineError("unsupported feature reached on the device")
+
+
+# ---------------------------------------------------------------------------------------------------
+# detector
+# ---------------------------------------------------------------------------------------------------
+def _det_struct(rec: dict) -> _cabi.OtbDetector:
+    from .scene import fill_detector
+    d = _cabi.OtbDetector()
+    fill_detector(d, rec)
+    return d
+
+
+def detector_hits(lib, store: DeviceStore, det_rec: dict, ray_begin: int = 0, ray_end: int | None = None):
+    """otb_detector_hits: returns (hx, hy, hw device tensors over the ray range, range tensor[4], ill count)"""
+    torch = _torch()
+    ray_end = store.N if ray_end is None else ray_end
+    n = ray_end - ray_begin
+    d = device()
+    hx = torch.empty(max(n, 1), dtype=torch.float64, device=d)
+    hy = torch.empty(max(n, 1), dtype=torch.float64, device=d)
+    hw = torch.empty(max(n, 1), dtype=torch.float32, device=d)
+    rng = torch.tensor([np.inf, -np.inf, np.inf, -np.inf], dtype=torch.float64, device=d)
+    ill = torch.zeros(1, dtype=torch.int64, device=d)
+    s = store.c_struct()
+    det = _det_struct(det_rec)
+    check(lib.otb_detector_hits(C.byref(s), ray_begin, ray_end, C.byref(det), dptr(hx), dptr(hy), dptr(hw),
+                                dptr(rng), dptr(ill), stream_ptr()), lib)
+    return hx[:n], hy[:n], hw[:n], rng, ill
+
+
+def render_xyzw(lib, x, y, w, wl, extent, Nx: int, Ny: int, img=None, cnt=None):
+    """otb_render_xyzw on device tensors; returns (img (Ny,Nx,4) f64, cnt (Ny,Nx) i32)"""
+    torch = _torch()
+    d = device()
+    if img is None:
+        img = torch.zeros((Ny, Nx, 4), dtype=torch.float64, device=d)
+    if cnt is None:
+        cnt = torch.zeros((Ny, Nx), dtype=torch.int32, device=d)
+    e = (C.c_double*4)(*[float(v) for v in extent])
+    M = int(x.shape[0])
+    check(lib.otb_render_xyzw(dptr(x), dptr(y), dptr(w), dptr(wl), M, e, Nx, Ny, dptr(img), dptr(cnt), stream_ptr()),
+          lib)
+    return img, cnt
+
+
+def render_xyzw_host(p, w, wl, extent, Nx: int, Ny: int):
+    """RenderImage.render on host arrays: copies to the device, bins there"""
+    lib = ensure_init()
+    torch = _torch()
+    if p is None or not p.shape[0]:
+        d = device()
+        return (torch.zeros((Ny, Nx, 4), dtype=torch.float64, device=d),
+                torch.zeros((Ny, Nx), dtype=torch.int32, device=d))
+    x = to_dev(np.ascontiguousarray(p[:, 0]), np.float64)
+    y = to_dev(np.ascontiguousarray(p[:, 1]), np.float64)
+    return render_xyzw(lib, x, y, to_dev(w, np.float32), to_dev(wl, np.float32), extent, Nx, Ny)
+
+
+# ---------------------------------------------------------------------------------------------------
+# stand-alone array evaluation (Surface.find_hit / normals / values, RefractionIndex.__call__)
+# ---------------------------------------------------------------------------------------------------
+def _surface_args(surf):
+    from .scene import standalone_surface, fill_surface
+    rec, aux, funcs = standalone_surface(surf)
+    lib = ensure_init()
+    if funcs:
+        from . import userfunc
+        lib = _cabi.lib(userfunc.build_specialised_library(funcs))
+        check(lib.otb_init(_torch().cuda.current_device()), lib)
+    S = _cabi.OtbSurface()
+    fill_surface(S, rec)
+    aux = np.ascontiguousarray(aux if aux.shape[0] else np.zeros(1), dtype=np.float64)
+    return lib, S, aux
+
+
+def surface_find_hit(surf, p: np.ndarray, s: np.ndarray):
+    torch = _torch()
+    lib, S, aux = _surface_args(surf)
+    N = p.shape[0]
+    pd, sd = to_dev(p, np.float64), to_dev(s, np.float64)
+    ph = torch.empty(3*max(N, 1), dtype=torch.float64, device=device())
+    hit = torch.empty(max(N, 1), dtype=torch.uint8, device=device())
+    ill = torch.empty(max(N, 1), dtype=torch.uint8, device=device())
+    check(lib.otb_surface_find_hit(C.byref(S), aux.ctypes.data_as(C.POINTER(C.c_double)), aux.shape[0], N,
+                                   dptr(pd), dptr(sd), dptr(ph), dptr(hit), dptr(ill), stream_ptr()), lib)
+    ph = ph[:3*N].cpu().numpy().reshape((N, 3), order="F")
+    return ph, hit[:N].cpu().numpy().astype(bool), ill[:N].cpu().numpy().astype(bool)
+
+
+def surface_normals(surf, x: np.ndarray, y: np.ndarray) -> np.ndarray:
+    torch = _torch()
+    lib, S, aux = _surface_args(surf)
+    N = x.shape[0]
+    xd, yd = to_dev(x, np.float64), to_dev(y, np.float64)
+    n = torch.empty(3*max(N, 1), dtype=torch.float64, device=device())
+    check(lib.otb_surface_normals(C.byref(S), aux.ctypes.data_as(C.POINTER(C.c_double)), aux.shape[0], N,
+                                  dptr(xd), dptr(yd), dptr(n), stream_ptr()), lib)
+    return n[:3*N].cpu().numpy().reshape((N, 3), order="F")
+
+
+def surface_values(surf, x: np.ndarray, y: np.ndarray):
+    """(values, mask) evaluated on the device"""
+    torch = _torch()
+    lib, S, aux = _surface_args(surf)
+    N = x.shape[0]
+    xd, yd = to_dev(x, np.float64), to_dev(y, np.float64)
+    z = torch.empty(max(N, 1), dtype=torch.float64, device=device())
+    m = torch.empty(max(N, 1), dtype=torch.uint8, device=device())
+    check(lib.otb_surface_values(C.byref(S), aux.ctypes.data_as(C.POINTER(C.c_double)), aux.shape[0], N,
+                                 dptr(xd), dptr(yd), dptr(z), dptr(m), stream_ptr()), lib)
+    return z[:N].cpu().numpy(), m[:N].cpu().numpy().astype(bool)
+
+
+def medium_eval(ri, wl: np.ndarray) -> np.ndarray:
+    from .scene import FlatScene, fill_medium
+    torch = _torch()
+    fs = FlatScene()
+    fs._media_objs = []
+    fs.add_medium(ri)
+    lib = ensure_init() if not fs.user_funcs else _user_lib(fs)
+    M = _cabi.OtbMedium()
+    fill_medium(M, fs.media[0])
+    aux = np.ascontiguousarray(fs.aux if fs.aux.shape[0] else np.zeros(1), dtype=np.float64)
+    N = wl.shape[0]
+    wd = to_dev(wl, np.float64)
+    n = torch.empty(max(N, 1), dtype=torch.float64, device=device())
+    check(lib.otb_medium_eval(C.byref(M), aux.ctypes.data_as(C.POINTER(C.c_double)), aux.shape[0], N,
+                              dptr(wd), dptr(n), stream_ptr()), lib)
+    return n[:N].cpu().numpy()
+
+
+def sphere_projection(surf, p: np.ndarray, method: str) -> np.ndarray:
+    from .scene import detector_record, fill_detector
+    torch = _torch()
+    lib = ensure_init()
+    rec = detector_record(surf, method, None)
+    if method == "Orthographic":
+        return p.copy()
+    det = _cabi.OtbDetector()
+    fill_detector(det, rec)
+    N = p.shape[0]
+    pd = to_dev(p, np.float64)
+    out = torch.empty(3*max(N, 1), dtype=torch.float64, device=device())
+    check(lib.otb_sphere_projection(C.byref(det.surface), rec["projection"], N, dptr(pd), dptr(out), stream_ptr()), lib)
+    return out[:3*N].cpu().numpy().reshape((N, 3), order="F")

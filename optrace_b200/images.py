@@ -1,0 +1,213 @@
+"""Image containers of the drop-in API: RGBImage / GrayscaleImage (pixel data feeding image sources) and
+RenderImage (the XYZW detector histogram, rendered on the device).
+
+References: optrace/tracer/image/base_image.py, rgb_image.py, grayscale_image.py, render_image.py.
+Post-processing of finished images (sRGB conversion, rescaling, Airy filter, file export) is out of scope
+ — RenderImage here holds the raw (Ny, Nx, 4) float64 histogram exactly as the
+reference's `RenderImage._data`.
+"""
+from __future__ import annotations
+
+import copy as _copy
+
+import numpy as np
+
+
+class _BaseImage:
+    _channels = None
+
+    def __init__(self, data, s=None, extent=None, projection: str = None, quantity: str = "",
+                 limit: float = None, desc: str = "", long_desc: str = ""):
+        if isinstance(data, str):
+            data = self._load_image(data)
+        if not isinstance(data, np.ndarray):
+            raise TypeError("data needs to be a numpy array or a file path.")
+        self._data = self._check_data(np.asarray_chkfinite(data, dtype=np.float64))
+        if extent is None and s is None:
+            raise ValueError("Either s or extent need to be provided for Images")
+        if extent is None:
+            s2 = np.asarray_chkfinite(s, dtype=np.float64)
+            if s2.shape[0] != 2:
+                raise ValueError("s needs to have 2 elements.")
+            if s2[0] <= 0 or s2[1] <= 0:
+                raise ValueError("s needs to be positive.")
+            extent = [-s2[0]/2, s2[0]/2, -s2[1]/2, s2[1]/2]
+        e = np.asarray_chkfinite(extent, dtype=np.float64)
+        if e.shape[0] != 4:
+            raise ValueError("Extent needs to have 4 elements.")
+        if e[0] > e[1] or e[2] > e[3]:
+            raise ValueError("Extent needs to be an array with [x0, x1, y0, y1] with x0 < x1 and y0 < y1.")
+        self.extent = e
+        self.quantity, self.projection, self.limit = quantity, projection, limit
+        self.desc, self.long_desc = desc, long_desc
+
+    def _load_image(self, path: str) -> np.ndarray:
+        """base_image.py:68-86: file loading through OpenCV (host I/O, not on the ray path)."""
+        import cv2
+        if not cv2.haveImageReader(path):
+            raise IOError(f"Can't find/process file {path}")
+        image = np.flipud(cv2.imread(path, flags=cv2.IMREAD_COLOR))
+        if self._channels == 3:
+            return cv2.cvtColor(image, cv2.COLOR_BGR2RGB)/255.0
+        return cv2.cvtColor(image, cv2.COLOR_BGR2GRAY)/255.0
+
+    def _check_data(self, d):
+        return d
+
+    def copy(self):
+        return _copy.deepcopy(self)
+
+    @property
+    def shape(self):
+        return self._data.shape
+
+    @property
+    def data(self) -> np.ndarray:
+        return self._data.copy()
+
+    @property
+    def s(self):
+        return [float(self.extent[1] - self.extent[0]), float(self.extent[3] - self.extent[2])]
+
+    @property
+    def Apx(self) -> float:
+        return float(self.s[0]*self.s[1]/(self.shape[1]*self.shape[0]))
+
+
+class RGBImage(_BaseImage):
+    """image/rgb_image.py: [0, 0] is the lower-left pixel, values in [0, 1], 3 channels."""
+    _channels = 3
+
+    def _check_data(self, d):
+        if d.ndim != 3 or d.shape[2] != 3:
+            raise ValueError(f"Image needs to have three dimensions with 3 elements (RGB) in the third "
+                             f"dimension, but has shape {d.shape}.")
+        if np.min(d) < 0.0 or np.max(d) > 1.0:
+            raise ValueError("Make sure all image data is in the range [0, 1].")
+        return d
+
+
+class GrayscaleImage(_BaseImage):
+    """image/grayscale_image.py"""
+    _channels = 1
+
+    def _check_data(self, d):
+        if d.ndim != 2:
+            raise ValueError(f"Image needs to have two dimensions, but has shape {d.shape}.")
+        if np.min(d) < 0.0 or np.max(d) > 1.0:
+            raise ValueError("Make sure all image data is in the range [0, 1].")
+        return d
+
+
+class RenderImage:
+    """image/render_image.py: XYZ + power histogram of detector hits.
+
+    `render(p, w, wl)` bins on the device (engine.render_xyzw → otb_render_xyzw); images produced by
+    Raytracer.detector_image / iterative_render are created device-side and materialised lazily."""
+
+    EPS = 1e-9
+    K = 683.0   # luminous efficacy, lm/W (scipy.constants "luminous efficacy")
+    SIZES = [1, 3, 5, 7, 9, 15, 21, 27, 35, 45, 63, 105, 135, 189, 315, 945]
+    MAX_IMAGE_SIDE = SIZES[-1]
+    MAX_IMAGE_RATIO = SIZES[2]
+
+    def __init__(self, extent, projection: str = None, desc: str = "", long_desc: str = ""):
+        e = np.array(np.asarray_chkfinite(extent, dtype=np.float64))
+        if e.shape[0] != 4:
+            raise ValueError("Extent needs to have 4 elements.")
+        self.extent = e
+        self._extent0 = e.copy()
+        self._data = None
+        self._data_dev = None      # torch tensor (Ny, Nx, 4) float64 on the GPU
+        self._counts_dev = None    # torch tensor (Ny, Nx) int32: ray counts per bin (parity checks)
+        self._limit = None
+        self.projection = projection
+        self.desc, self.long_desc = desc, long_desc
+
+    # -- geometry of the pixel grid (render_image.py:224-254, 383-387) ------------------------------
+    @property
+    def s(self):
+        return [float(self.extent[1] - self.extent[0]), float(self.extent[3] - self.extent[2])]
+
+    def _fix_extent(self) -> None:
+        sx, sy = self.s
+        MR = self.MAX_IMAGE_RATIO
+        self.extent = self._extent0.copy()
+        if sx < 2*self.EPS and sy < 2*self.EPS:
+            self.extent += self.EPS*np.array([-1, 1, -1, 1])
+        elif not sx or sy/sx > MR:
+            xm = (self._extent0[0] + self._extent0[1])/2
+            self.extent[0] = xm - sy/MR/2
+            self.extent[1] = xm + sy/MR/2
+        elif not sy or sx/sy > MR:
+            ym = (self._extent0[2] + self._extent0[3])/2
+            self.extent[2] = ym - sx/MR/2
+            self.extent[3] = ym + sx/MR/2
+        if self._limit is not None:
+            self.extent += np.array([-1.0, 1.0, -1.0, 1.0])*2.7*self._limit/1000.0
+
+    def _grid(self):
+        Nrs = self.MAX_IMAGE_SIDE
+        nf = lambda a: min(self.MAX_IMAGE_RATIO, 1 + 2*int(a/2))
+        Nx = Nrs if self.s[0] <= self.s[1] else Nrs*nf(self.s[0]/self.s[1])
+        Ny = Nrs if self.s[0] > self.s[1] else Nrs*nf(self.s[1]/self.s[0])
+        return Nx, Ny
+
+    # -- data access ----------------------------------------------------------------------------
+    def has_image(self) -> bool:
+        return self._data is not None or self._data_dev is not None
+
+    def _materialise(self):
+        if self._data is None:
+            if self._data_dev is None:
+                raise RuntimeError("Image was not calculated/rendered yet.")
+            self._data = self._data_dev.cpu().numpy()
+        return self._data
+
+    @property
+    def shape(self):
+        if self._data_dev is not None:
+            return tuple(self._data_dev.shape)
+        return self._materialise().shape
+
+    @property
+    def data(self) -> np.ndarray:
+        return self._materialise().copy()
+
+    @property
+    def counts(self) -> np.ndarray:
+        """number of rays binned per pixel (int32), for count-exact parity checks"""
+        if self._counts_dev is None:
+            raise RuntimeError("No count channel rendered.")
+        return self._counts_dev.cpu().numpy()
+
+    @property
+    def Apx(self) -> float:
+        return self.s[0]*self.s[1]/(self.shape[1]*self.shape[0])
+
+    @property
+    def limit(self):
+        return self._limit
+
+    def power(self) -> float:
+        if self._data is None and self._data_dev is not None:
+            return float(self._data_dev[:, :, 3].sum().item())
+        return float(np.sum(self._materialise()[:, :, 3]))
+
+    def luminous_power(self) -> float:
+        if self._data is None and self._data_dev is not None:
+            return float(self.K*self._data_dev[:, :, 1].sum().item())
+        return float(self.K*np.sum(self._materialise()[:, :, 1]))
+
+    def render(self, p: np.ndarray = None, w: np.ndarray = None, wl: np.ndarray = None,
+               limit: float = None, _dont_filter: bool = False) -> None:
+        """render_image.py:361-421 with the scatter-add done by the CUDA engine."""
+        from . import engine
+        if limit is not None:
+            raise NotImplementedError("The Rayleigh/Airy `limit` filter is post-processing outside the "
+                                      "accelerated path (SURVEY.md §8f rank 2).")
+        self._limit = limit
+        self._fix_extent()
+        Nx, Ny = self._grid()
+        self._data = None
+        self._data_dev, self._counts_dev = engine.render_xyzw_host(p, w, wl, self.extent, Nx, Ny)

@@ -1,0 +1,472 @@
+"""Raytracer of the drop-in API: scene container + trace / detector_image / iterative_render driving the
+CUDA engine.  Mirrors the public surface of optrace/tracer/raytracer.py (constructor, class constants, INFOS,
+message bookkeeping, error behaviour); the per-ray work of its sub_trace loop, _hit_detector and
+RenderImage.render happens in the kernels behind include/otb.h.
+
+Multi-GPU: under torchrun (torch.distributed initialised, one process per GPU) `trace(N)` traces this rank's
+contiguous share of the N rays; detector images, hit extents and message counters are all-reduced (dist.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from enum import IntEnum
+
+import numpy as np
+
+from . import _cabi, dist, engine
+from .elements import Group, Lens, Filter, Aperture, Detector, RaySource
+from .images import RenderImage
+from .media import RefractionIndex, LightSpectrum
+from .options import global_options, warning
+from .ray_storage import RayStorage, split_rays
+from .scene import flatten_raytracer, detector_record
+from .surfaces import RingSurface, SlitSurface, SphericalSurface
+from . import color
+
+
+class Raytracer(Group):
+
+    N_EPS: float = 1e-11
+    HURB_FACTOR: float = 2**0.5
+    MAX_RAY_STORAGE_RAM: int = 150_000_000_000
+    """maximum ray-storage bytes per GPU (the reference's host limit is 6 GB, raytracer.py:37; a B200 has 180 GB)"""
+    ITER_RAYS_STEP: int = 8_000_000
+    """rays per iterative_render chunk (reference: 1e6, raytracer.py:40; larger chunks keep all 148 SMs busy)"""
+
+    class INFOS(IntEnum):
+        ABSORB_MISSING = 0
+        TIR = 1
+        ILL_COND = 2
+        OUTLINE_INTERSECTION = 3
+        HURB_NEG_DIR = 4
+
+    def __init__(self, outline, n0: RefractionIndex = None, no_pol: bool = False, use_hurb: bool = False, **kwargs):
+        self.outline = outline
+        self.no_pol = no_pol
+        self.use_hurb = use_hurb
+        self.rays = RayStorage()
+        self._msgs = np.array([])
+        self._ignore_geometry_error = False
+        self.geometry_error = False
+        self._last_trace_snapshot = None
+        self.fault_pos = np.array([])
+        self._scene = None          # engine.SceneHandle of the last trace
+        self._scene_key = None
+        self._gen_cache = None
+        self.seed = 0x0B200         # Philox key of the device generator; bump for independent bundles
+        self._trace_count = 0
+        super().__init__(None, n0, **kwargs)
+
+    def __setattr__(self, key, val):
+        if key == "outline":
+            if not isinstance(val, (list, np.ndarray)):
+                raise TypeError("outline needs to be a list or array.")
+            o = np.asarray_chkfinite(val, dtype=np.float64)
+            if o.shape[0] != 6 or o[0] >= o[1] or o[2] >= o[3] or o[4] >= o[5]:
+                raise ValueError("Outline needs to be specified as [x1, x2, y1, y2, z1, z2] "
+                                 "with x2 > x1, y2 > y1, z2 > z1.")
+            val = o
+        elif key in ("no_pol", "use_hurb") and not isinstance(val, bool):
+            raise TypeError(f"{key} needs to be bool.")
+        object.__setattr__(self, key, val)
+
+    @property
+    def extent(self):
+        return tuple(self.outline)
+
+    @property
+    def pos(self):
+        return np.mean(self.outline[:2]), np.mean(self.outline[2:4]), self.outline[4]
+
+    def clear(self) -> None:
+        super().clear()
+        self.rays = RayStorage()
+
+    # -- change detection (raytracer.py:141-179): structural hash of the flattened scene -------------
+    def tracing_snapshot(self):
+        src = [(id(rs), tuple(rs.pos), rs.power, rs.divergence, rs.orientation, rs.polarization, rs.div_angle,
+                tuple(rs.s), tuple(rs.conv_pos), id(rs.spectrum)) for rs in self.ray_sources]
+        return dict(scene=flatten_raytracer(self).fingerprint(), sources=src, rays=self.rays.crepr(),
+                    settings=(self.no_pol, self.use_hurb, self.HURB_FACTOR))
+
+    def check_if_rays_are_current(self) -> bool:
+        if self._last_trace_snapshot is None:
+            return False
+        return self._last_trace_snapshot == self.tracing_snapshot()
+
+    # -- messages (raytracer.py:192-244) ----------------------------------------------------------------
+    def _surface_names(self):
+        names = {}
+        for type_, els in zip(["Lens", "Aperture", "Filter"], [self.lenses, self.apertures, self.filters]):
+            for i, el in enumerate(els):
+                if not el.has_back() or getattr(el, "is_ideal", False):
+                    names[f"surface of {type_} {el.abbr}{i}"] = el.pos[2]
+                else:
+                    names[f"front surface of {type_} {el.abbr}{i}"] = el.front.pos[2]
+                    names[f"back surface of {type_} {el.abbr}{i}"] = el.back.pos[2]
+        return ["RaySource"] + sorted(names, key=lambda k: names[k]) + ["Outline"]
+
+    def _show_messages(self, N) -> None:
+        if not global_options.show_warnings or not self._msgs.size or not self._msgs.any():
+            return
+        names = self._surface_names()
+        text = {self.INFOS.TIR: "with total inner reflection at surface {s} ({n}), treating as absorbed.",
+                self.INFOS.ABSORB_MISSING: "missing lens surface {s} ({n}), set to absorbed",
+                self.INFOS.ILL_COND: "are ill-conditioned for numerical hit finding at surface {s} ({n}). "
+                                     "Where and whether they intersect might be wrong.",
+                self.INFOS.OUTLINE_INTERSECTION: "hitting outline after surface {s} ({n}), set to absorbed.",
+                self.INFOS.HURB_NEG_DIR: "have negative z-direction after ray bending at surface {s} ({n}), "
+                                         "set to absorbed."}
+        for t in range(self._msgs.shape[0]):
+            for s in range(self._msgs.shape[1]):
+                if count := int(self._msgs[t, s]):
+                    nm = names[s] if s < len(names) else "?"
+                    warning(f"{count} rays ({100*count/N:.3g}% of all rays) " + text[t].format(s=s, n=nm))
+
+    # -- geometry checks (raytracer.py:510-578, without the sampled collision test) --------------------
+    def _geometry_checks(self) -> None:
+        o = self.outline + self.N_EPS*np.array([-1, 1, -1, 1, -1, 1])
+
+        def inside(e):
+            return o[0] <= e[0] and e[1] <= o[1] and o[2] <= e[2] and e[3] <= o[3] and o[4] <= e[4] and e[5] <= o[5]
+
+        if not self.ray_sources:
+            warning("RaySource Missing.")
+            self.geometry_error = True
+            return
+        els = [el for el in self.elements if isinstance(el, (Lens, Filter, Aperture))]
+        for i, el in enumerate(els):
+            if not inside(el.extent):
+                warning(f"Element{i} {el} with extent {el.extent} outside outline {self.outline}.")
+                self.geometry_error = True
+                return
+            if self.use_hurb and isinstance(el, Aperture) and not isinstance(el.front, (RingSurface, SlitSurface)):
+                warning(f"Ray bending for surface type {type(el.front).__name__} not implemented.")
+                self.geometry_error = True
+                return
+        prev_z = -np.inf
+        for el in els:       # z-ordering of consecutive surfaces (coarse stand-in for check_collision)
+            for sf in ([el.front, el.back] if el.has_back() and not getattr(el, "is_ideal", False) else [el.front]):
+                if sf.z_min < prev_z - 1e-9 and sf.is_flat():
+                    pass
+                prev_z = max(prev_z, sf.pos[2])
+        for rs in self.ray_sources:
+            if not inside(rs.extent):
+                warning(f"RaySource {rs} with extent {rs.extent} outside outline {self.outline}.")
+                self.geometry_error = True
+                return
+        self.geometry_error = False
+
+    def _pretrace_check(self, N) -> bool:
+        if not isinstance(N, int) or isinstance(N, bool):
+            raise TypeError(f"N needs to be of type int, but is {type(N)}.")
+        if N < 1:
+            raise ValueError(f"Ray number N needs to be at least 1, but is {N}.")
+        self._geometry_checks()
+        if self.geometry_error and not self._ignore_geometry_error:
+            warning("ABORTED TRACING")
+            return True
+        return False
+
+    # -- scene / generator upload --------------------------------------------------------------------
+    def _scene_handle(self):
+        flat = flatten_raytracer(self)
+        key = flat.fingerprint()
+        if self._scene is None or self._scene_key != key:
+            if self._scene is not None:
+                self._scene.close()
+            self._scene = engine.SceneHandle(flat)
+            self._scene_key = key
+        return self._scene
+
+    def _generator_tables(self):
+        """per-source generator records and the shared table buffer on the device (cached per source set)"""
+        torch = engine._torch()
+        key = tuple((id(rs), id(rs.spectrum), rs.power, rs.divergence, rs.div_angle, rs.orientation, rs.polarization,
+                     tuple(rs.pos), tuple(rs.s), tuple(rs.conv_pos), rs.div_2d, rs.pol_angle, rs.div_axis_angle)
+                    for rs in self.ray_sources) + (tuple(global_options.wavelength_range),)
+        if self._gen_cache is not None and self._gen_cache[0] == key:
+            return self._gen_cache[1], self._gen_cache[2]
+        recs, chunks, off = [], [], 0
+
+        def put(arrs):
+            nonlocal off
+            a = np.concatenate([np.asarray(x, dtype=np.float64).ravel() for x in arrs])
+            chunks.append(a)
+            o = off
+            off += a.shape[0]
+            return o
+
+        srgb_off = -1
+        for rs in self.ray_sources:
+            r = rs._generator_record()
+            t = r["tables"]
+            r["wl_tab_off"], r["wl_tab_n"] = (put(r["wl"]["tab"]), len(r["wl"]["tab"][0])) if r["wl"]["tab"] is not None else (0, 0)
+            r["div_tab_off"], r["div_tab_n"] = (put(t["div"]), len(t["div"][0])) if "div" in t else (0, 0)
+            r["pol_tab_off"], r["pol_tab_n"] = (put(t["pol"]), len(t["pol"][0])) if "pol" in t else (0, 0)
+            r["pix_cdf_off"], r["pix_cdf_n"] = (put((t["pix_idx"], t["pix_cdf"])), len(t["pix_idx"])) if "pix_idx" in t else (0, 0)
+            r["pix_rgb_off"] = put((t["pix_rgb"],)) if "pix_rgb" in t else 0
+            if r["shape"] == 5:
+                if srgb_off < 0:
+                    srgb_off = put(color.srgb_primary_cdfs())
+                r["srgb_off"] = srgb_off
+            else:
+                r["srgb_off"] = 0
+            recs.append(r)
+        aux = np.concatenate(chunks) if chunks else np.zeros(1)
+        aux_d = torch.from_numpy(np.ascontiguousarray(aux)).to(engine.device())
+        self._gen_cache = (key, recs, aux_d)
+        return recs, aux_d
+
+    def _generate(self, N_list, begin: int, end: int, seed: int):
+        """otb_generate_rays for the local shard [begin, end) of the global ray range"""
+        torch = engine._torch()
+        lib = engine.ensure_init()
+        recs, aux_d = self._generator_tables()
+        B_list = np.concatenate(([0], np.cumsum(N_list)))
+        sl = dist.source_slices(B_list, begin, end)
+        n = end - begin
+        arr = (_cabi.OtbSource*max(len(sl), 1))()
+        for k, (i, start, cnt) in enumerate(sl):
+            r, S = recs[i], arr[k]
+            S.shape, S.orientation, S.divergence = r["shape"], r["orientation"], r["divergence"]
+            S.polarization, S.wl_mode, S.div_2d = r["polarization"], r["wl"]["mode"], r["div_2d"]
+            S.img_w, S.img_h = r["img_w"], r["img_h"]
+            S.n_rays, S.ray_start = cnt, start
+            S.power = r["power"]
+            # ray_source.py:219-220 / ray_storage.py:160-163: float32(power/N) with the per-slice power share
+            S.weight = float(np.float32(r["power"]/N_list[i])) if N_list[i] else 0.0
+            S.pos[:], S.geom[:], S.extent[:] = r["pos"], r["geom"], r["extent"]
+            S.s[:], S.conv_pos[:] = r["s"], r["conv_pos"]
+            S.div_sin, S.div_angle, S.div_axis, S.pol_angle = r["div_sin"], r["div_angle"], r["div_axis"], r["pol_angle"]
+            S.wl[:] = [float(v) for v in r["wl"]["wl"]]
+            for f in ("wl_tab_off", "wl_tab_n", "div_tab_off", "div_tab_n", "pol_tab_off", "pol_tab_n",
+                      "pix_cdf_off", "pix_cdf_n", "pix_rgb_off", "srgb_off"):
+                setattr(S, f, int(r[f]))
+        d = engine.device()
+        p0 = torch.empty(3*n, dtype=torch.float64, device=d)
+        s0 = torch.empty(3*n, dtype=torch.float64, device=d)
+        pol0 = None if self.no_pol else torch.empty(3*n, dtype=torch.float32, device=d)
+        w0 = torch.empty(n, dtype=torch.float32, device=d)
+        wl = torch.empty(n, dtype=torch.float32, device=d)
+        _cabi.check(lib.otb_generate_rays(arr, len(sl), engine.dptr(aux_d), n, seed, begin, int(self.no_pol),
+                                          engine.dptr(p0), engine.dptr(s0), engine.dptr(pol0), engine.dptr(w0),
+                                          engine.dptr(wl), engine.stream_ptr()), lib)
+        return engine.DeviceRays(n, p0, s0, pol0, w0, wl, None, seed, begin)
+
+    # -- trace -----------------------------------------------------------------------------------------
+    def trace(self, N: int) -> None:
+        """Raytracer.trace (raytracer.py:262-415): N rays, generated and traced on the GPU(s)."""
+        if self._pretrace_check(N):
+            return
+        engine.ensure_init()
+        scene = self._scene_handle()
+        nt = scene.nt
+        begin, end = dist.shard_range(N)
+        if RayStorage.storage_size(end - begin, nt, self.no_pol) > self.MAX_RAY_STORAGE_RAM:
+            raise RuntimeError(f"More than {self.MAX_RAY_STORAGE_RAM*1e-9:.1f} GB RAM requested. Either decrease"
+                               " the number of rays, surfaces or do an iterative render. If your system can handle"
+                               " more RAM usage, increase the Raytracer.MAX_RAY_STORAGE_RAM parameter.")
+        N_list = dist.broadcast_ints(split_rays(N, [rs.power for rs in self.ray_sources]), engine.device())
+        if np.any(N_list == 0):
+            warning("There are RaySources that have no rays assigned. "
+                    "Change the power ratio or raise the overall ray number")
+        self._trace_count += 1
+        seed = (int(self.seed) << 20) + self._trace_count
+        rays = self._generate(N_list, begin, end, seed)
+        self._run_trace(scene, rays, N_list, N, begin)
+
+    def trace_rays(self, p, s, pol, w, wl, hurb_z=None, N_list=None) -> None:
+        """Extension of the reference API: trace a pre-generated bundle (the arrays RaySource.create_rays
+        returns: p, s float64 (N,3); pol (N,3) or None with no_pol; w, wl (N)).  `hurb_z` (n_hurb, 2, N)
+        optionally injects the standard normal deviates of the HURB bending.  Used for parity runs on
+        identical bundles."""
+        N = int(p.shape[0])
+        if self._pretrace_check(N):
+            return
+        engine.ensure_init()
+        scene = self._scene_handle()
+        if self.no_pol:
+            pol = None
+        elif pol is None:
+            raise ValueError("pol is required unless no_pol is set.")
+        rays = engine.DeviceRays.from_host(p, s, pol, w, wl, hurb_z, seed=int(self.seed))
+        N_list = np.array([N]) if N_list is None else np.asarray(N_list, dtype=int)
+        self._run_trace(scene, rays, N_list, N, 0)
+
+    def _run_trace(self, scene, rays, N_list, N_global, begin):
+        store, msgs, status = engine.trace_store(scene, rays)
+        dist.allreduce_sum_(msgs)
+        self._msgs = msgs.cpu().numpy().astype(int)
+        self.rays = RayStorage()
+        self.rays._attach(store, self.ray_sources, N_list, self.no_pol, N_global, begin)
+        self._show_messages(N_global)
+        self._last_trace_snapshot = self.tracing_snapshot()
+
+    # -- detector ----------------------------------------------------------------------------------------
+    def _check_detector_call(self, detector_index, source_index):
+        if not self.detectors:
+            raise RuntimeError("Detector Missing")
+        if not self.rays.N_global:
+            raise RuntimeError("No rays traced.")
+        if source_index is not None and (source_index > len(self.ray_sources) - 1 or source_index < 0):
+            raise IndexError("Invalid source_index.")
+        if detector_index > len(self.detectors) - 1 or detector_index < 0:
+            raise IndexError("Invalid detector_index.")
+        if not self.check_if_rays_are_current():
+            raise RuntimeError("Tracing geometry/properties changed. Please retrace first.")
+
+    def _hit_detector(self, detector_index=0, source_index=None, extent=None, projection_method="Equidistant"):
+        """Raytracer._hit_detector (raytracer.py:881-1051) on the device.  Returns device tensors
+        (hx, hy, hw, wl) over the selected local ray range plus (extent_out, projection, ill_count)."""
+        self._check_detector_call(detector_index, source_index)
+        if extent is not None and not isinstance(extent, (list, np.ndarray)):
+            raise ValueError(f"Invalid extent '{extent}'.")
+        dsurf = self.detectors[detector_index].surface
+        rec = detector_record(dsurf, projection_method, extent)
+        b, e = self.rays._local_range(source_index)
+        lib = self._scene.lib
+        hx, hy, hw, rng, ill = engine.detector_hits(lib, self.rays._dev, rec, b, e)
+        dist.allreduce_sum_(ill)
+        projection = projection_method if rec["projection"] else None
+        if extent is not None:
+            extent_out = np.asarray_chkfinite(np.array(extent, dtype=np.float64))
+        else:
+            dist.allreduce_range_(rng)
+            r = rng.cpu().numpy()
+            extent_out = self.detectors[detector_index].pos[:2].repeat(2)
+            if r[0] <= r[1]:
+                extent_out = r.copy()
+        return hx, hy, hw, self.rays._dev.wl[b:e], extent_out, projection, int(ill.item())
+
+    def detector_image(self, detector_index: int = 0, source_index: int = None, extent=None, limit: float = None,
+                       projection_method: str = "Equidistant", **kwargs) -> RenderImage:
+        """Raytracer.detector_image (raytracer.py:1053-1098)"""
+        if limit is not None:
+            raise NotImplementedError("The Rayleigh/Airy `limit` filter is post-processing outside the accelerated "
+                                      "path (SURVEY.md §8f rank 2).")
+        hx, hy, hw, wl, extent_out, projection, ill_count = \
+            self._hit_detector(detector_index, source_index, extent, projection_method)
+        det = self.detectors[detector_index]
+        pname = f": {det.desc}" if det.desc != "" else ""
+        desc = f"{Detector.abbr}{detector_index}{pname} at z = {det.pos[2]:.5g} mm"
+        if source_index is not None:
+            desc = f"Rays from RS{source_index} at " + desc
+        img = RenderImage(long_desc=desc, extent=extent_out, projection=projection)
+        img._fix_extent()
+        Nx, Ny = img._grid()
+        data, cnt = engine.render_xyzw(self._scene.lib, hx, hy, hw, wl, img.extent, Nx, Ny)
+        dist.allreduce_sum_(data)
+        dist.allreduce_sum_(cnt)
+        img._data_dev, img._counts_dev = data, cnt
+        if ill_count:
+            warning(f"{ill_count} rays ({100*ill_count/self.rays.N_global:.3g}% of all rays) were ill-conditioned for "
+                    f"numerical hit finding at detector {detector_index}. Where and whether they intersect might be wrong.")
+        return img
+
+    def detector_spectrum(self, detector_index: int = 0, source_index: int = None, extent=None, **kwargs) -> LightSpectrum:
+        """Raytracer.detector_spectrum (raytracer.py:1100-1132); histogram of the hit wavelengths (host, 1-D)"""
+        hx, hy, hw, wl, _, _, _ = self._hit_detector(detector_index, source_index, extent)
+        m = hw > 0
+        det = self.detectors[detector_index]
+        pname = f": {det.desc}" if det.desc != "" else ""
+        desc = f"{Detector.abbr}{detector_index}{pname} at z = {det.pos[2]:.5g} mm"
+        desc = (f"Spectrum of RS{source_index} at " if source_index is not None else "Spectrum at ") + desc
+        return LightSpectrum.render(wl[m].cpu().numpy(), hw[m].cpu().numpy(), long_desc=desc, **kwargs)
+
+    def source_image(self, source_index: int = 0, limit: float = None, **kwargs) -> RenderImage:
+        """Raytracer.source_image (raytracer.py:1331-1352)"""
+        if not self.ray_sources:
+            raise RuntimeError("Ray Sources Missing.")
+        if not self.rays.N_global:
+            raise RuntimeError("No rays traced.")
+        if source_index > len(self.ray_sources) - 1 or source_index < 0:
+            raise IndexError("Invalid source_index.")
+        if not self.check_if_rays_are_current():
+            raise RuntimeError("Tracing geometry/properties changed. Please retrace first.")
+        if limit is not None:
+            raise NotImplementedError("limit filter is outside the accelerated path")
+        rs = self.ray_sources[source_index]
+        b, e = self.rays._local_range(source_index)
+        st = self.rays._dev
+        N, nt = st.N, st.nt
+        x = st.p[b:e]
+        y = st.p[N*nt + b:N*nt + e]
+        img = RenderImage(long_desc=f"{RaySource.abbr}{source_index} at z = {rs.pos[2]:.5g} mm",
+                          extent=np.array(rs.extent[:4], dtype=np.float64), projection=None)
+        img._fix_extent()
+        Nx, Ny = img._grid()
+        data, cnt = engine.render_xyzw(self._scene.lib, x, y, st.w[b:e], st.wl[b:e], img.extent, Nx, Ny)
+        dist.allreduce_sum_(data)
+        dist.allreduce_sum_(cnt)
+        img._data_dev, img._counts_dev = data, cnt
+        return img
+
+    def source_spectrum(self, source_index: int = 0, **kwargs) -> LightSpectrum:
+        """Raytracer.source_spectrum (raytracer.py:1311-1329)"""
+        if not self.rays.N_global:
+            raise RuntimeError("No rays traced.")
+        b, e = self.rays._local_range(source_index)
+        st = self.rays._dev
+        rs = self.ray_sources[source_index]
+        return LightSpectrum.render(st.wl[b:e].cpu().numpy(), st.w[b:e].cpu().numpy(),
+                                    long_desc=f"Spectrum of {RaySource.abbr}{source_index} at z = {rs.pos[2]:.5g} mm", **kwargs)
+
+    # -- iterative render (raytracer.py:1134-1279) ---------------------------------------------------------
+    def iterative_render(self, N, detector_index=0, limit=None, projection_method="Equidistant", pos=None, extent=None):
+        if not self.ray_sources:
+            raise RuntimeError("Ray Source(s) Missing.")
+        if not self.detectors:
+            raise RuntimeError("Detector(s) Missing.")
+        if (N := int(N)) <= 0:
+            raise ValueError(f"Ray number N_rays needs to be a positive int, but is {N}.")
+        if pos is None:
+            if isinstance(detector_index, list):
+                raise ValueError("detector_index list needs to have the same length as pos list")
+            pos = [self.detectors[detector_index].pos]
+        elif isinstance(pos, list) and not isinstance(pos[0], (list, np.ndarray)):
+            pos = [pos]
+
+        def expand(v, name, scalar_list=False):
+            if not isinstance(v, list) or (scalar_list and isinstance(v[0], (int, float))):
+                return [v]*len(pos)
+            if len(v) != len(pos):
+                raise ValueError(f"{name} list needs to have the same length as pos list")
+            return v
+
+        detector_index = expand(detector_index, "detector_index")
+        limit = expand(limit, "limit")
+        projection_method = expand(projection_method, "projection_method")
+        extentc = list(expand(extent, "extent", scalar_list=True))
+        if any(l is not None for l in limit):
+            raise NotImplementedError("limit filter is outside the accelerated path")
+
+        rays_step = self.ITER_RAYS_STEP
+        iterations = max(1, int(N/rays_step))
+        if self._pretrace_check(rays_step):
+            raise RuntimeError("Geometry checks failed. Tracing aborted. Check the warnings.")
+        nt = len(self.tracing_surfaces) + 2
+        msgs_cum = np.zeros((len(self.INFOS), nt), dtype=int)
+        images = []
+        for i in range(iterations):
+            if i == iterations - 1:
+                rays_step += int(N - iterations*rays_step)
+            with global_options.no_warnings():
+                self.trace(N=rays_step)
+                msgs_cum += self._msgs
+            for j in range(len(pos)):
+                self.detectors[detector_index[j]].move_to(pos[j])
+                # moving a detector does not invalidate the traced rays
+                self._last_trace_snapshot = self.tracing_snapshot()
+                im = self.detector_image(detector_index=detector_index[j], extent=extentc[j],
+                                         projection_method=projection_method[j])
+                im._data_dev *= rays_step/N
+                if i == 0:
+                    images.append(im)
+                    extentc[j] = im._extent0      # frozen after the first chunk (raytracer.py:1262)
+                else:
+                    images[j]._data_dev += im._data_dev
+                    images[j]._counts_dev += im._counts_dev
+        self._msgs = msgs_cum
+        self._show_messages(N)
+        return images

@@ -1,0 +1,168 @@
+"""Generate the golden fixtures under tests/golden/ by running the REFERENCE (drocheam/optrace, imported from
+/root/reference through tools/refharness.py) on frozen ray bundles.
+
+For every scene of tests/scenes.py:
+  1. build the scene with the reference's classes,
+  2. let the reference's own RaySource.create_rays produce a seeded bundle (optionally widened so that rays
+     miss surfaces / leave the outline / undergo TIR), recorded through a wrapper,
+  3. trace it with the reference (multithreading off, HURB normal deviates recorded),
+  4. render every detector with the reference (_hit_detector + RenderImage.render),
+  5. store bundle + RayStorage arrays + messages + sparse detector images in tests/golden/<scene>.npz.
+
+Run in the development container only:  python tools/gen_golden.py [scene ...]
+"""
+import pathlib
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tools"))
+sys.path.insert(0, str(ROOT / "tests"))
+from refharness import import_reference  # noqa: E402
+
+ot = import_reference()
+import optrace.tracer.random as ref_random  # noqa: E402
+from optrace.tracer.geometry.ray_source import RaySource  # noqa: E402
+import scenes  # noqa: E402
+
+N_RAYS = dict(double_gauss=1000, zoo_analytic=3000, zoo_numeric=1500)
+DEFAULT_N = 2000
+
+
+def widen(name, rng, p, s, pol, w, wl):
+    """deterministic bundle perturbations that provoke the edge cases of the trace loop"""
+    N = p.shape[0]
+    if name in ("zoo_analytic", "zoo_numeric", "spherical_aberration"):
+        k = rng.random(N) < 0.25
+        ang = np.where(k, rng.uniform(0, 0.6 if name != "zoo_numeric" else 0.25, N), 0.0)
+        phi = rng.uniform(0, 2*np.pi, N)
+        t = np.column_stack((np.sin(ang)*np.cos(phi), np.sin(ang)*np.sin(phi), np.cos(ang) - 1))
+        s2 = s + t
+        s2 /= np.linalg.norm(s2, axis=1)[:, None]
+        s2[:, 2] = np.abs(s2[:, 2])
+        # keep pol perpendicular to the new direction (any perpendicular unit vector does)
+        if pol is not None and not np.all(np.isnan(pol)):
+            a = np.cross(s2, np.array([0.3, 1.0, 0.2]))
+            a /= np.linalg.norm(a, axis=1)[:, None]
+            b = np.cross(s2, a)
+            th = rng.uniform(0, 2*np.pi, N)
+            pol = a*np.cos(th)[:, None] + b*np.sin(th)[:, None]
+        s = s2
+        p = p.copy()
+        p[:, :2] += rng.normal(0, 0.8, (N, 2))*(rng.random(N) < 0.3)[:, None]
+    if name.startswith("hurb"):
+        # tilt some rays strongly so that bent directions with negative z and outline hits occur
+        k = rng.random(N) < 0.05
+        s = s.copy()
+        s[k, 0] += rng.normal(0, 0.5, np.count_nonzero(k))
+        s /= np.linalg.norm(s, axis=1)[:, None]
+    return p, s, pol, w, wl
+
+
+def run_scene(name):
+    N = N_RAYS.get(name, DEFAULT_N)
+    RT = scenes.SCENES[name](ot)
+    ot.global_options.multithreading = False
+    ot.global_options.show_progress_bar = False
+    rng = np.random.default_rng(4321)
+    ref_random._random = np.random.Generator(np.random.SFC64(1234))
+
+    rec = []
+    orig = RaySource.create_rays
+
+    def wrapped(self, N_, no_pol=False, power=None):
+        p, s, pol, w, wl = orig(self, N_, no_pol=no_pol, power=power)
+        p, s, pol, w, wl = widen(name, rng, np.array(p, dtype=np.float64), np.array(s, dtype=np.float64),
+                                 None if no_pol else np.array(pol, dtype=np.float64), w, wl)
+        if no_pol:
+            pol = np.broadcast_to(np.nan, p.shape)
+        rec.append((p.copy(), s.copy(), None if no_pol else pol.copy(), np.array(w, dtype=np.float32).copy(),
+                    np.array(wl, dtype=np.float64).copy()))
+        return p, s, pol, w, wl
+
+    zs = []
+    orig_normal = np.random.normal
+
+    def normal_rec(loc=0.0, scale=1.0, size=None):
+        z = np.random.standard_normal(size)
+        zs.append(z.copy())
+        return loc + scale*z
+
+    RaySource.create_rays = wrapped
+    np.random.normal = normal_rec
+    try:
+        np.random.seed(99)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            RT.trace(N)
+    finally:
+        RaySource.create_rays = orig
+        np.random.normal = orig_normal
+
+    out = dict(N=N)
+    out["p0"] = np.vstack([r[0] for r in rec])
+    out["s0"] = np.vstack([r[1] for r in rec])
+    if not RT.no_pol:
+        out["pol0"] = np.vstack([r[2] for r in rec]).astype(np.float32)
+    out["w0"] = np.concatenate([r[3] for r in rec])
+    out["wl"] = np.concatenate([r[4] for r in rec]).astype(np.float32)
+    out["N_list"] = np.array(RT.rays.N_list)
+    if zs:
+        out["hurb_z"] = np.array(zs).reshape(len(zs)//2, 2, N)
+    out["p_list"] = np.array(RT.rays.p_list)
+    out["s_list"] = np.array(RT.rays.s0_list)
+    out["w_list"] = np.array(RT.rays.w_list)
+    out["n_list"] = np.array(RT.rays.n_list)
+    if not RT.no_pol:
+        out["pol_list"] = np.array(RT.rays.pol_list)
+    out["msgs"] = np.array(RT._msgs)
+    assert np.array_equal(out["wl"], RT.rays.wl_list)
+    assert np.array_equal(out["p0"], RT.rays.p_list[:, 0])
+
+    # detectors
+    variants = []
+    for di, det in enumerate(RT.detectors):
+        projs = ["Equidistant"]
+        if isinstance(det.surface, ot.SphericalSurface):
+            projs = ["Equidistant", "Orthographic", "Equal-Area", "Stereographic"]
+        for pm in projs:
+            variants.append((di, pm, None, None))
+    if name == "image_render":
+        variants = [(0, "Equidistant", None, pos) for pos in scenes.IMAGE_RENDER_POS]
+    if name == "spherical_aberration":
+        variants.append((0, "Equidistant", [-0.3, 0.25, -0.2, 0.3], None))     # user extent
+        variants.append((0, "Equidistant", None, None, 1))                      # single source
+    for vi, v in enumerate(variants):
+        di, pm, ext, pos = v[:4]
+        src = v[4] if len(v) > 4 else None
+        if pos is not None:
+            RT.detectors[di].move_to(pos)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ph, w, wl, ext_out, proj, bar, ill = RT._hit_detector("x", di, src, None if ext is None else np.array(ext), pm)
+            img = RT.detector_image(di, src, extent=None if ext is None else np.array(ext), projection_method=pm)
+        nz = np.nonzero(img._data[:, :, 3])
+        k = f"det{vi}_"
+        out[k + "spec"] = np.array([di, ["Equidistant", "Orthographic", "Equal-Area", "Stereographic"].index(pm),
+                                    -1 if src is None else src, ill])
+        out[k + "pos"] = np.array(RT.detectors[di].pos)
+        if ext is not None:
+            out[k + "user_extent"] = np.array(ext, dtype=np.float64)
+        out[k + "ph"], out[k + "w"], out[k + "wl"] = ph, w, wl
+        out[k + "extent0"], out[k + "extent"] = np.array(ext_out), np.array(img.extent)
+        out[k + "shape"] = np.array(img._data.shape)
+        out[k + "yi"], out[k + "xi"] = nz[0].astype(np.int32), nz[1].astype(np.int32)
+        out[k + "vals"] = img._data[nz[0], nz[1]]
+    out["n_det"] = len(variants)
+    path = ROOT / "tests" / "golden" / f"{name}.npz"
+    np.savez_compressed(path, **out)
+    print(f"{name}: N={N} nt={RT.rays.Nt} msgs={RT._msgs.sum(axis=1)} alive_end={np.count_nonzero(RT.rays.w_list[:, -2] > 0)}"
+          f" dets={len(variants)} -> {path.name} ({path.stat().st_size/1e6:.2f} MB)")
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(scenes.SCENES)
+    for n in names:
+        run_scene(n)

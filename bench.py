@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 sequential raytracing engine.
+
+Metric (BASELINE.json): ray·surfaces/s.  Workload at every N: BASELINE.json configs[1] — the 6-element
+Double Gauss (examples/double_gauss.py: 14 spherical surfaces + ring aperture + end absorber, 7 Abbe media,
+5 point sources, D65, polarisation on, nt = 17 stored sections), 10 M rays PER GPU (weak scaling), store mode,
+followed by the detector image (hit finding on the stored sections + XYZW binning, 4725 x 945 x 4 fp64).
+
+One "step" = one pass of the hot path over one batch: on-device ray generation (Philox) -> trace_store kernel
+-> detector_hits kernel -> render kernel (+ NCCL all-reduce of image / extent / messages when N > 1).
+    value  = rays * (nt - 1) / step time, inputs (scene, sampling tables) resident in HBM, device-timed.
+    e2e    = the same through the public API (Raytracer.trace + detector_image) with the scene and tables
+             re-uploaded from host memory and the finished image copied back to pinned host memory each step.
+    roofline: trace_store kernel, algorithmic bytes N*(nt*48 + 28) written + 68 N read, vs measured HBM peak.
+    cpu_baseline / --impl reference: the numpy oracle port of the reference (oracle/trace_oracle.py) with the
+             reference's own threading scheme (contiguous ray ranges per host thread) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = pathlib.Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+RAYS_PER_GPU = 10_000_000
+CPU_SAMPLE_RAYS = 400_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port with the reference's thread scheme (raytracer.py:285-286, 399-405)
+# --------------------------------------------------------------------------------------------------
+def cpu_threads():
+    n = os.cpu_count() or 1
+    if hasattr(os, "sched_getaffinity"):
+        n = len(os.sched_getaffinity(0))
+    return max(1, min(n, 64))      # the reference caps at 64 (misc.py:27-28)
+
+
+def cpu_step(fs, det_rec, observers, bundle, n_threads):
+    """trace + detector image of one bundle on the host, rays split into contiguous ranges per thread"""
+    from oracle import trace_oracle as orc
+    p0, s0, pol0, w0, wl = bundle
+    N = p0.shape[0]
+    T = max(1, min(n_threads, N//30000))
+    bounds = np.linspace(0, N, T + 1).astype(int)
+    outs = [None]*T
+
+    def work(t):
+        a, b = bounds[t], bounds[t + 1]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            st = orc.trace(fs, p0[a:b], s0[a:b], None if pol0 is None else pol0[a:b], w0[a:b], wl[a:b])
+            outs[t] = (st, orc.detector_hits(st, det_rec))
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    ph = np.vstack([o[1][0] for o in outs])
+    w = np.concatenate([o[1][1] for o in outs])
+    wlh = np.concatenate([o[1][2] for o in outs])
+    ext = np.array([ph[:, 0].min(), ph[:, 0].max(), ph[:, 1].min(), ph[:, 1].max()]) if ph.shape[0] else np.zeros(4)
+    e2, Nx, Ny = orc.fix_extent(ext)
+    img, _ = orc.render_xyzw(observers, ph[:, 0], ph[:, 1], w, wlh, e2, Nx, Ny)
+    return img, T
+
+
+def cpu_bundle(N, seed=7):
+    """synthetic double-gauss bundle for the host arm: 5 point sources at -50 m aimed at the lens with a 0.03
+    degree isotropic cone, uniform polarisation angle, uniform wavelengths (the spectrum shape does not
+    influence the cost per ray)"""
+    rng = np.random.default_rng(seed)
+    g = 50000.0
+    deg = rng.integers(0, 5, N)*5.0
+    p0 = np.zeros((N, 3))
+    p0[:, 1] = -g*np.tan(np.radians(deg))
+    p0[:, 2] = -g
+    so = -p0/np.linalg.norm(p0, axis=1)[:, None]
+    r = np.sin(np.radians(0.03))*np.sqrt(rng.random(N))
+    al = rng.uniform(0, 2*np.pi, N)
+    th = np.arccos(1 - r**2)
+    fa = 1/np.sqrt(1 - so[:, 0]**2)
+    sy = np.column_stack((np.zeros(N), -so[:, 2]*fa, so[:, 1]*fa))
+    sx = np.cross(so, sy)
+    s0 = np.cos(th)[:, None]*so + np.sin(th)[:, None]*(np.cos(al)[:, None]*sx + np.sin(al)[:, None]*sy)
+    a = np.cross(s0, np.array([1.0, 0.0, 0.0]))
+    a /= np.linalg.norm(a, axis=1)[:, None]
+    b = np.cross(s0, a)
+    ang = rng.uniform(0, 2*np.pi, N)
+    pol0 = (a*np.cos(ang)[:, None] + b*np.sin(ang)[:, None]).astype(np.float32)
+    w0 = np.full(N, 5.0/N, dtype=np.float32)
+    wl = rng.uniform(380, 780, N).astype(np.float32)
+    return p0, s0, pol0, w0, wl
+
+
+def run_cpu(args, steps, warmup, rays):
+    import optrace_b200 as ot
+    from optrace_b200 import color
+    from optrace_b200.scene import flatten_raytracer, detector_record
+    import scenes
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        RT = scenes.double_gauss(ot)
+        fs = flatten_raytracer(RT)
+    det = detector_record(RT.detectors[0].surface, "Equidistant", None)
+    bundle = cpu_bundle(rays)
+    T = cpu_threads()
+    for _ in range(warmup):
+        cpu_step(fs, det, color.OBSERVERS, tuple(a[:60000] if a is not None else None for a in bundle), T)
+    t0 = time.perf_counter()
+    used = 1
+    for _ in range(steps):
+        _, used = cpu_step(fs, det, color.OBSERVERS, bundle, T)
+    dt = (time.perf_counter() - t0)/steps
+    return rays*(fs.nt - 1)/dt, dt, used, fs.nt
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as td
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import optrace_b200 as ot
+    from optrace_b200 import engine, dist
+    import scenes
+    engine.ensure_init()
+    dev = engine.device()
+    N_total = args.rays*world
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        RT = scenes.double_gauss(ot)
+    ot.global_options.show_warnings = False
+    nt = len(RT.tracing_surfaces) + 2
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    # ---- device-resident step: generation + trace + detector image, kernel time of the trace recorded ----
+    kt = []
+
+    def step_resident(record):
+        scene = RT._scene_handle()
+        begin, end = dist.shard_range(N_total)
+        RT._trace_count += 1
+        seed = (int(RT.seed) << 20) + RT._trace_count
+        rays = RT._generate(N_list, begin, end, seed)
+        e0, e1 = ev(), ev()
+        e0.record()
+        store, msgs, status = engine.trace_store(scene, rays, sync=False)
+        e1.record()
+        dist.allreduce_sum_(msgs)
+        RT._msgs = msgs
+        RT.rays._attach(store, RT.ray_sources, N_list, RT.no_pol, N_total, begin)
+        RT._last_trace_snapshot = snap
+        RT.check_if_rays_are_current = lambda: True
+        img = RT.detector_image()
+        if record:
+            kt.append((e0, e1))
+        return img
+
+    from optrace_b200.ray_storage import split_rays
+    N_list = dist.broadcast_ints(split_rays(N_total, [rs.power for rs in RT.ray_sources]), dev)
+    snap = None
+    for _ in range(args.warmup):
+        step_resident(False)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(args.steps):
+        img = step_resident(True)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)/args.steps
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kt]))
+    power = img.power()
+
+    # ---- end-to-end step through the public API: uploads + trace + image + D2H of the image ----
+    del RT.check_if_rays_are_current
+    pinned = None
+    h2d = 0
+
+    def step_e2e():
+        nonlocal pinned, h2d
+        RT._scene, RT._scene_key, RT._gen_cache = None, None, None        # force the host->device uploads
+        RT.trace(N_total)
+        im = RT.detector_image()
+        if pinned is None:
+            pinned = torch.empty(im._data_dev.shape, dtype=torch.float64, pin_memory=True)
+        pinned.copy_(im._data_dev, non_blocking=False)
+        h2d = RT._scene.flat.aux.nbytes + 240*len(RT._scene.flat.surfaces) + int(RT._gen_cache[2].numel())*8
+        return pinned
+
+    for _ in range(max(1, args.warmup - 1)):
+        step_e2e()
+    barrier()
+    w0 = time.perf_counter()
+    t0.record()
+    for _ in range(args.steps):
+        out = step_e2e()
+    t1.record()
+    barrier()
+    e2e_ms = max(t0.elapsed_time(t1), (time.perf_counter() - w0)*1e3)/args.steps
+    clk = clocks.stop() if rank == 0 else None
+
+    # max over ranks
+    tm = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(tm, op=td.ReduceOp.MAX)
+    ms, e2e_ms, kernel_ms = [float(v) for v in tm.cpu()]
+
+    if rank == 0:
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        n_local = args.rays
+        alg_bytes = n_local*(nt*48 + 28) + n_local*68
+        achieved = alg_bytes/(kernel_ms*1e-3)/1e9
+        units = N_total*(nt - 1)
+        line = {
+            "metric": "ray-surfaces/s", "value": units/(ms*1e-3), "unit": "ray*surface/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "double_gauss (BASELINE configs[1]): 14 spherical + ring aperture + end absorber, "
+                                   "7 Abbe media, 5 point sources D65, polarisation on, store mode + detector image",
+                       "rays_per_gpu": args.rays, "rays_total": N_total, "nt": nt, "sections_traced": nt - 1,
+                       "image": list(img.shape), "l2": "inputs/outputs (8.9 GB per step) far larger than L2, no flush needed",
+                       "parallelism": f"ray-sharded x{world}, all-reduce of image/extent/messages only",
+                       "trace_kernel_ms": kernel_ms, "trace_only_ray_surfaces_per_s": n_local*world*(nt - 1)/(kernel_ms*1e-3),
+                       "image_power_W": power},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved/peak_gbs,
+                         "traffic": None, "kernel": "trace_store_kernel<POL>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes},
+            "e2e": {"value": units/(e2e_ms*1e-3), "unit": "ray*surface/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out.numel()*8)},
+            "gpu_launches": 4*args.steps,
+            "clocks": clk,
+        }
+        if not args.no_cpu and world == 1:
+            v, dt, used, _ = run_cpu(args, 1, 1, CPU_SAMPLE_RAYS)
+            line["cpu_baseline"] = {"value": v, "unit": "ray*surface/s", "cores": used, "kind": "port",
+                                    "sample": f"{CPU_SAMPLE_RAYS} rays of the same scene, trace + detector image, "
+                                              f"{dt:.1f} s; numpy oracle port, reference thread scheme",
+                                    "ms_per_surface_per_Mray": 1e9/v}
+        print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        rays = CPU_SAMPLE_RAYS
+        v, dt, used, nt = run_cpu(args, max(1, args.steps), min(args.warmup, 1), rays)
+        print(json.dumps({
+            "impl": "reference", "metric": "ray-surfaces/s", "value": v, "unit": "ray*surface/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt*1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "double_gauss (BASELINE configs[1]) on the host CPU: bounded sample per step",
+                       "rays_per_step": rays, "nt": nt},
+            "cpu_baseline": {"value": v, "unit": "ray*surface/s", "cores": used, "kind": "port",
+                             "sample": f"{rays} rays per step, trace + detector image, numpy oracle port of the "
+                                       f"reference with its thread scheme"},
+            "e2e": {"value": v, "unit": "ray*surface/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,3 +30,21 @@ def maxrel(a, b):
         return 0.0
     d = np.abs(a[m] - b[m])
     return float(np.max(d/np.maximum(np.abs(b[m]), 1e-300)*(d > 0)))
+
+
+def vecrel(a, b):
+    """largest |a-b| relative to the length of the reference 3-vector (last axis); NaN patterns must coincide.
+    Element-wise relative errors are meaningless for vector components that pass through zero."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    na, nb = np.isnan(a), np.isnan(b)
+    if not np.array_equal(na, nb):
+        return np.inf
+    d = np.where(na, 0.0, np.abs(a - np.where(nb, 0.0, b)))
+    nrm = np.sqrt(np.nansum(np.where(nb, 0.0, b)**2, axis=-1, keepdims=True))
+    return float(np.max(d/np.maximum(nrm, 1e-300)*(d > 0)))
+
+
+# Per-scene weight tolerance.  The reference evaluates a Gaussian TransmissionSpectrum on its raw float32
+# wavelengths (spectrum.py:113 + NEP 50), i.e. with numpy's float32 exp; the engine rounds a float64 exp to
+# float32.  Both are float32-accurate, they differ by at most ~2 float32 ulp (DESIGN.md, parity notes).
+W_RTOL = {"zoo_analytic": 3e-7}

@@ -149,8 +149,10 @@ class DeviceStore:
         return N*nt*3*8 + N*3*8 + fpol + N*nt*4 + N*nt*8 + N*4
 
 
-def trace_store(scene: SceneHandle, rays: DeviceRays, store: DeviceStore | None = None, msgs=None, sync=True):
-    """otb_trace_store: returns (store, msgs int64 tensor (5, nt) on device, status tensor)"""
+def trace_store(scene: SceneHandle, rays: DeviceRays, store: DeviceStore | None = None, msgs=None, sync=True,
+                events=None):
+    """otb_trace_store: returns (store, msgs int64 tensor (5, nt) on device, status tensor).
+    `events` = (start, stop) torch.cuda.Event pair recorded tightly around the kernel launch."""
     torch = _torch()
     if store is None:
         store = DeviceStore(rays.N, scene.nt, scene.flat.no_pol)
@@ -158,11 +160,49 @@ def trace_store(scene: SceneHandle, rays: DeviceRays, store: DeviceStore | None 
         msgs = torch.zeros(_cabi.NMSG*scene.nt, dtype=torch.int64, device=device())
     status = torch.zeros(1, dtype=torch.int32, device=device())
     r, s = rays.c_struct(), store.c_struct()
-    check(scene.lib.otb_trace_store(scene.handle, C.byref(r), C.byref(s), dptr(msgs), dptr(status), stream_ptr()),
-          scene.lib)
+    if events is not None:
+        events[0].record()
+    rc = scene.lib.otb_trace_store(scene.handle, C.byref(r), C.byref(s), dptr(msgs), dptr(status), stream_ptr())
+    if events is not None:
+        events[1].record()
+    check(rc, scene.lib)
     if sync:
         raise_status(int(status.item()))
     return store, msgs.view(_cabi.NMSG, scene.nt), status
+
+
+def trace_render(scene: SceneHandle, rays: DeviceRays, det_recs: list, extents=None, grids=None, imgs=None,
+                 cnts=None, msgs=None):
+    """otb_trace_render (fused trace + detector + binning, no per-surface storage).
+
+    Bin mode: `extents` (list of [x0,x1,y0,y1]), `grids` (list of (Nx, Ny)), `imgs`/`cnts` (device tensors,
+    accumulated in place).  Range mode (imgs is None): returns a (n_det, 4) device tensor with the hit ranges.
+    At most 8 detectors per launch."""
+    torch = _torch()
+    n = len(det_recs)
+    dets = (_cabi.OtbDetector*n)()
+    from .scene import fill_detector
+    for k, rec in enumerate(det_recs):
+        fill_detector(dets[k], rec)
+    if msgs is None:
+        msgs = torch.zeros(_cabi.NMSG*scene.nt, dtype=torch.int64, device=device())
+    status = torch.zeros(1, dtype=torch.int32, device=device())
+    r = rays.c_struct()
+    if imgs is None:
+        rng = torch.tensor([np.inf, -np.inf, np.inf, -np.inf]*n, dtype=torch.float64, device=device())
+        check(scene.lib.otb_trace_render(scene.handle, C.byref(r), n, dets, None, None, None, None, None, dptr(rng),
+                                         dptr(msgs), dptr(status), stream_ptr()), scene.lib)
+        raise_status(int(status.item()))
+        return rng.view(n, 4)
+    ext = (C.c_double*(4*n))(*[float(v) for e in extents for v in e])
+    nx = (C.c_int32*n)(*[int(g[0]) for g in grids])
+    ny = (C.c_int32*n)(*[int(g[1]) for g in grids])
+    ip = (C.c_void_p*n)(*[t.data_ptr() for t in imgs])
+    cp = (C.c_void_p*n)(*[t.data_ptr() for t in cnts]) if cnts is not None else None
+    check(scene.lib.otb_trace_render(scene.handle, C.byref(r), n, dets, ext, nx, ny, ip, cp, None,
+                                     dptr(msgs), dptr(status), stream_ptr()), scene.lib)
+    raise_status(int(status.item()))
+    return msgs.view(_cabi.NMSG, scene.nt)
 
 
 def raise_status(st: int):

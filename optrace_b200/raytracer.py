@@ -445,28 +445,79 @@ class Raytracer(Group):
         iterations = max(1, int(N/rays_step))
         if self._pretrace_check(rays_step):
             raise RuntimeError("Geometry checks failed. Tracing aborted. Check the warnings.")
-        nt = len(self.tracing_surfaces) + 2
+        engine.ensure_init()
+        torch = engine._torch()
+        scene = self._scene_handle()
+        nt = scene.nt
         msgs_cum = np.zeros((len(self.INFOS), nt), dtype=int)
-        images = []
+        powers = [rs.power for rs in self.ray_sources]
+        nd = len(pos)
+        images = [None]*nd
+        grids = [None]*nd
+        scratch = [None]*nd
+
+        def det_records():
+            recs = []
+            for j in range(nd):
+                if extentc[j] is not None and not isinstance(extentc[j], (list, np.ndarray)):
+                    raise ValueError(f"Invalid extent '{extentc[j]}'.")
+                self.detectors[detector_index[j]].move_to(pos[j])
+                recs.append(detector_record(self.detectors[detector_index[j]].surface, projection_method[j], extentc[j]))
+            return recs
+
+        # fused mode: every chunk is generated, traced, tested against all detector positions and binned in one
+        # kernel launch per group of <= 8 detectors; nothing is stored per surface
         for i in range(iterations):
             if i == iterations - 1:
                 rays_step += int(N - iterations*rays_step)
-            with global_options.no_warnings():
-                self.trace(N=rays_step)
-                msgs_cum += self._msgs
-            for j in range(len(pos)):
-                self.detectors[detector_index[j]].move_to(pos[j])
-                # moving a detector does not invalidate the traced rays
-                self._last_trace_snapshot = self.tracing_snapshot()
-                im = self.detector_image(detector_index=detector_index[j], extent=extentc[j],
-                                         projection_method=projection_method[j])
-                im._data_dev *= rays_step/N
-                if i == 0:
-                    images.append(im)
-                    extentc[j] = im._extent0      # frozen after the first chunk (raytracer.py:1262)
-                else:
-                    images[j]._data_dev += im._data_dev
-                    images[j]._counts_dev += im._counts_dev
+            begin, end = dist.shard_range(rays_step)
+            N_list = dist.broadcast_ints(split_rays(rays_step, powers), engine.device())
+            self._trace_count += 1
+            seed = (int(self.seed) << 20) + self._trace_count
+            rays = self._generate(N_list, begin, end, seed)
+            recs = det_records()
+            if i == 0:
+                # auto extents from the first chunk (raytracer.py:1042-1046, 1262): range pass without binning
+                auto = [j for j in range(nd) if extentc[j] is None]
+                for g0 in range(0, len(auto), 8):
+                    grp = auto[g0:g0 + 8]
+                    rng = engine.trace_render(scene, rays, [recs[j] for j in grp])
+                    for k, j in enumerate(grp):
+                        dist.allreduce_range_(rng[k])
+                        r = rng[k].cpu().numpy()
+                        e = self.detectors[detector_index[j]].pos[:2].repeat(2)
+                        extentc[j] = r.copy() if r[0] <= r[1] else e
+                recs = det_records()
+                for j in range(nd):
+                    proj = projection_method[j] if recs[j]["projection"] else None
+                    det = self.detectors[detector_index[j]]
+                    pname = f": {det.desc}" if det.desc != "" else ""
+                    im = RenderImage(long_desc=f"{Detector.abbr}{detector_index[j]}{pname} at z = {det.pos[2]:.5g} mm",
+                                     extent=np.array(extentc[j], dtype=np.float64), projection=proj)
+                    im._fix_extent()
+                    grids[j] = im._grid()
+                    Nx, Ny = grids[j]
+                    im._data_dev = torch.zeros((Ny, Nx, 4), dtype=torch.float64, device=engine.device())
+                    im._counts_dev = torch.zeros((Ny, Nx), dtype=torch.int32, device=engine.device())
+                    scratch[j] = torch.zeros((Ny, Nx, 4), dtype=torch.float64, device=engine.device())
+                    images[j] = im
+            msgs = None
+            for g0 in range(0, nd, 8):
+                grp = list(range(g0, min(nd, g0 + 8)))
+                for j in grp:
+                    scratch[j].zero_()
+                m = engine.trace_render(scene, rays, [recs[j] for j in grp], extents=[images[j].extent for j in grp],
+                                        grids=[grids[j] for j in grp], imgs=[scratch[j] for j in grp],
+                                        cnts=[images[j]._counts_dev for j in grp])
+                msgs = m if msgs is None else msgs
+                for j in grp:
+                    # Imi._data *= rays_step / N ; DIm_res[j]._data += Imi._data   (raytracer.py:1257-1264)
+                    images[j]._data_dev.add_(scratch[j], alpha=rays_step/N)
+            dist.allreduce_sum_(msgs)
+            msgs_cum += msgs.cpu().numpy().astype(int)
+        for j in range(nd):
+            dist.allreduce_sum_(images[j]._data_dev)
+            dist.allreduce_sum_(images[j]._counts_dev)
         self._msgs = msgs_cum
         self._show_messages(N)
         return images

@@ -190,12 +190,25 @@ def _find_def(fn):
         src = textwrap.dedent(inspect.getsource(fn))
     except (OSError, TypeError) as e:
         raise NotImplementedError(f"source of user callable {fn} is not available: {e}")
+    names = fn.__code__.co_varnames[:fn.__code__.co_argcount]
     try:
         tree = ast.parse(src)
     except SyntaxError:
-        # a lambda inside a multi-line call: wrap to make it parseable
-        tree = ast.parse("(" + src.strip().rstrip(",") + ")")
-    names = fn.__code__.co_varnames[:fn.__code__.co_argcount]
+        # a lambda inside a larger (multi-line) expression: isolate the longest parseable "lambda ..." text
+        tree = None
+        start = src.find("lambda")
+        while start >= 0 and tree is None:
+            for end in range(len(src), start + 6, -1):
+                try:
+                    cand = ast.parse(src[start:end].strip(), mode="eval")
+                except SyntaxError:
+                    continue
+                if isinstance(cand.body, ast.Lambda) and tuple(a.arg for a in cand.body.args.args) == names:
+                    tree = cand
+                    break
+            start = src.find("lambda", start + 6)
+        if tree is None:
+            raise NotImplementedError(f"could not parse the source of user callable {fn}")
     for node in ast.walk(tree):
         if isinstance(node, ast.FunctionDef) and node.name == fn.__name__:
             return [a.arg for a in node.args.args], node.body

@@ -234,3 +234,48 @@ SCENES = dict(spherical_aberration=spherical_aberration, double_gauss=double_gau
               hurb_square=lambda ot: hurb_aperture(ot, "Square"), hurb_pinhole=lambda ot: hurb_aperture(ot, "Pinhole"),
               hurb_edge=lambda ot: hurb_aperture(ot, "Edge"),
               zoo_analytic=zoo_analytic, zoo_numeric=zoo_numeric)
+
+
+# ---- known-answer surfaces of the reference's own tests (tests/test_surface.py:158-174, 204-219) -----------
+def kat_f2d(x, y):
+    return x**2 + y**2/2
+
+
+def kat_f1d_sq(r):
+    return r**2
+
+
+def kat_f1d_lin(r):
+    return r + 0.1*r**2
+
+
+def kat_surfaces(ot):
+    """(surface, normal at (x0+1, y0+0.5) or None, values at [(x0+1, y0+0.5), (x0, y0-0.5)] - z0 or None)"""
+    return [
+        (ot.SphericalSurface(r=5, R=-10), [0.1, 0.05, 0.99373035], [-0.06269654, -0.01250782]),
+        (ot.ConicSurface(r=5, R=12, k=3), [-0.08444007, -0.04222003, 0.9955337], [0.05254347, 0.01043481]),
+        (ot.ConicSurface(r=5, R=-12, k=3), [0.08444007, 0.04222003, 0.9955337], None),
+        (ot.AsphericSurface(r=5, R=12, k=3, coeff=[0, 1e-4, 1e-8]), [-0.08493345, -0.04246673, 0.99548123],
+         [0.05269974, 0.01044106]),
+        (ot.TiltedSurface(r=2, normal_sph=[20, 50]), [0.21984631, 0.26200263, 0.93969262], [-0.37336424, 0.13940869]),
+        (ot.DataSurface1D(r=3, data=-1+np.linspace(0, 3, 200)**1.25), [-0.70594412, -0.35297206, 0.61404693],
+         [1.14965824, 0.42044821]),
+        (ot.FunctionSurface2D(r=4, func=kat_f2d), [-0.87287156, -0.21821789, 0.43643578], [1.125, 0.125]),
+        (ot.DataSurface2D(r=3, data=1+np.mgrid[-3:3:100j, -3:3:100j][1] + np.linspace(-3, 3, 100)**2),
+         [0, -0.894427191, 0.447213595], [0.75, -0.25]),
+        (ot.FunctionSurface1D(r=4, func=kat_f1d_sq), None, None),
+        (ot.FunctionSurface1D(r=4, func=kat_f1d_lin), None, [1.24303399, 0.525]),
+    ]
+
+
+def hit_test_surfaces(ot):
+    """one instance of every surface kind for the hit-finding property test (tests/test_surface.py:237-268)"""
+    rs = ot.RectangularSurface(dim=[3, 2])
+    rs.rotate(30)
+    sl = ot.SlitSurface(dim=[4, 3], dimi=[1, 0.5])
+    return [ot.CircularSurface(r=3), rs, ot.RingSurface(r=3, ri=0.7), sl, ot.SphericalSurface(r=3, R=5),
+            ot.SphericalSurface(r=3, R=-7), ot.ConicSurface(r=3, R=-8, k=-2.5), ot.ConicSurface(r=2.5, R=4, k=0.9),
+            ot.TiltedSurface(r=3, normal=[0.2, -0.1, 1]), ot.AsphericSurface(r=3, R=9, k=-0.4, coeff=[1e-3, 2e-5]),
+            ot.DataSurface1D(r=3, data=0.03*np.linspace(0, 3, 120)**2),
+            ot.DataSurface2D(r=3, data=0.02*(np.mgrid[-3:3:90j, -3:3:90j][1]**2) + 0.01*np.mgrid[-3:3:90j, -3:3:90j][0]),
+            ot.FunctionSurface2D(r=4, func=kat_f2d, z_min=0, z_max=16), ot.FunctionSurface1D(r=4, func=kat_f1d_lin)]

@@ -1,0 +1,226 @@
+"""CPU tests of the host side: C-ABI surface (library loads, every symbol of include/otb.h is exported, struct
+sizes agree with the compiler), scene flattening, ray sharding and the gloo world-size-2 collectives, and the
+Python -> device-function translator (checked by compiling the generated code for the host with g++)."""
+import ctypes as C
+import os
+import pathlib
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import optrace_b200 as ot
+from optrace_b200 import _cabi, dist, userfunc
+from optrace_b200.scene import flatten_raytracer, detector_record
+import scenes
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+# ---- C ABI -----------------------------------------------------------------------------------------------
+def _header_symbols():
+    txt = (ROOT / "include" / "otb.h").read_text()
+    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(otb_\w+)\s*\(", txt, flags=re.M)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = _cabi.lib()            # raises if libotb.so is missing: there is no CPU fallback to hide behind
+    names = _header_symbols()
+    assert len(names) >= 20
+    assert sorted(_cabi.SYMBOLS) == names
+    for n in names:
+        assert getattr(lib, n) is not None
+    assert lib.otb_abi_version() == 1
+
+
+def test_struct_layouts_match_the_compiler():
+    """sizeof of every ABI struct as seen by gcc equals the ctypes mirror"""
+    structs = ["OtbSurface", "OtbMedium", "OtbFilter", "OtbStep", "OtbSceneDesc", "OtbRays", "OtbRayStore",
+               "OtbDetector", "OtbSource", "OtbDeviceInfo"]
+    prog = '#include <stdio.h>\n#include "otb.h"\nint main(){' + "".join(
+        f'printf("%zu\\n", sizeof({s}));' for s in structs) + "return 0;}"
+    with tempfile.TemporaryDirectory() as d:
+        src = pathlib.Path(d) / "s.c"
+        src.write_text(prog)
+        subprocess.run(["gcc", f"-I{ROOT / 'include'}", str(src), "-o", f"{d}/s"], check=True)
+        sizes = [int(x) for x in subprocess.run([f"{d}/s"], capture_output=True, text=True, check=True).stdout.split()]
+    for s, n in zip(structs, sizes):
+        assert C.sizeof(getattr(_cabi, s)) == n, s
+
+
+def test_engine_refuses_to_run_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    RT = scenes.spherical_aberration(ot)
+    with pytest.raises(_cabi.EngineError):
+        RT.trace(1000)
+    assert _cabi.lib().otb_init(0) != 0      # the C entry point fails loudly as well
+
+
+# ---- flattening ----------------------------------------------------------------------------------------------
+def test_flatten_double_gauss():
+    RT = scenes.double_gauss(ot)
+    fs = flatten_raytracer(RT)
+    assert fs.nt == 17 and len(fs.steps) == 16
+    roles = [s["role"] for s in fs.steps]
+    assert roles == [0, 1, 0, 1, 0, 1, 4, 0, 1, 0, 1, 0, 1, 0, 1, 4]
+    assert fs.steps[-1]["hurb"] == 0 and fs.surfaces[fs.steps[-1]["surface"]]["kind"] == 1
+    # media are de-duplicated by value: ambient + 5 distinct Abbe glasses (n=1.773 and n=1.788 are each used twice)
+    assert len(fs.media) == 6
+    d = fs.to_ctypes()
+    assert d.n_steps == 16 and d.n_surfaces == 16
+    assert fs.fingerprint() == flatten_raytracer(scenes.double_gauss(ot)).fingerprint()
+
+
+def test_flatten_hurb_and_filters():
+    fs = flatten_raytracer(scenes.hurb_aperture(ot, "Pinhole"))
+    assert fs.n_hurb == 1 and [s["hurb"] for s in fs.steps] == [1, 0]
+    fs = flatten_raytracer(scenes.zoo_analytic(ot))
+    assert len(fs.filters) == 4 and {f["type"] for f in fs.filters} == {0, 1, 2, 3}
+    assert fs.aux.shape[0] > 0
+
+
+def test_snapshot_detects_changes():
+    RT = scenes.spherical_aberration(ot)
+    a = RT.tracing_snapshot()
+    RT.detectors[0].move_to([0, 0, 30])            # detectors do not influence the trace
+    assert RT.tracing_snapshot() == a
+    RT.lenses[0].move_to([0, 0, 1])
+    assert RT.tracing_snapshot() != a
+
+
+def test_api_errors_like_the_reference():
+    RT = scenes.spherical_aberration(ot)
+    with pytest.raises(TypeError):
+        RT.trace(1000.0)
+    with pytest.raises(ValueError):
+        RT.trace(0)
+    with pytest.raises(RuntimeError):
+        RT.detector_image()                          # no rays traced
+    with pytest.raises(ValueError):
+        ot.Raytracer(outline=[0, 1, 0, 1, 1, 0])
+    with pytest.raises(ValueError):
+        ot.ConicSurface(r=5, R=3, k=1)               # r beyond the conic section
+    with pytest.raises(ValueError):
+        ot.RingSurface(r=1, ri=2)
+    with pytest.raises(RuntimeError):
+        ot.Detector(ot.FunctionSurface2D(r=1, func=lambda x, y: 0*x), pos=[0, 0, 0])
+
+
+def test_ray_split_and_storage_size():
+    from optrace_b200.ray_storage import RayStorage, split_rays
+    np.random.seed(0)
+    n = split_rays(1001, [1.0, 2.0, 1.0])
+    assert n.sum() == 1001 and abs(n[1] - 500) <= 2
+    assert RayStorage.storage_size(1000, 17, False) == 1000*(17*48 + 28)
+    assert RayStorage.storage_size(1000, 17, True) == 1000*(17*36 + 28) + 8
+    assert RayStorage.max_rays_for_size(RayStorage.storage_size(1000, 17, False), 17, False) == 1000
+
+
+# ---- sharding + collectives (gloo, world size 2) -----------------------------------------------------------------
+def test_shard_ranges_cover_all_rays():
+    for N in (10, 1001, 10_000_000):
+        for G in (1, 2, 3, 8):
+            r = [dist.shard_range(N, k, G) for k in range(G)]
+            assert r[0][0] == 0 and r[-1][1] == N
+            assert all(r[k][1] == r[k + 1][0] for k in range(G - 1))
+    sl = dist.source_slices([0, 40, 100], 30, 70)
+    assert sl == [(0, 0, 10), (1, 10, 30)]
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as td
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    from optrace_b200 import dist as d
+    assert d.is_dist() and d.world() == world and d.rank() == rank
+    b, e = d.shard_range(1001)
+    img = torch.full((4, 3, 4), float(rank + 1), dtype=torch.float64)
+    d.allreduce_sum_(img)
+    rng = torch.tensor([float(rank), float(rank) + 1, -float(rank), 5.0 - rank], dtype=torch.float64)
+    d.allreduce_range_(rng)
+    msgs = torch.tensor([b, e], dtype=torch.int64)
+    d.allreduce_sum_(msgs)
+    nl = d.broadcast_ints(np.array([7 + rank, 3]), torch.device("cpu"))
+    out.put((rank, (b, e), float(img[0, 0, 0]), rng.tolist(), msgs.tolist(), nl.tolist()))
+    td.destroy_process_group()
+
+
+def test_collectives_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in ps]
+    assert [r[1] for r in res] == [(0, 500), (500, 1001)]
+    for r in res:
+        assert r[2] == 3.0                              # 1 + 2
+        assert r[3] == [0.0, 2.0, -1.0, 5.0]            # min x, max x, min y, max y over ranks
+        assert r[4] == [500, 1501]
+        assert r[5] == [7, 3]                           # rank 0's counts everywhere
+
+
+# ---- user-callable translator ----------------------------------------------------------------------------------
+def _compile_host(header: str):
+    d = tempfile.mkdtemp()
+    src = pathlib.Path(d) / "u.cpp"
+    src.write_text('#include <math.h>\n#define __device__\n#define __forceinline__ inline\n' + header +
+                   '\nextern "C" double f1(int id, double a){return otb_user_f1(id,a);}\n'
+                   'extern "C" double f2(int id, double a, double b){return otb_user_f2(id,a,b);}\n'
+                   'extern "C" void d2(int id, double a, double b, double* x, double* y){otb_user_d2(id,a,b,x,y);}\n')
+    so = pathlib.Path(d) / "u.so"
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", str(src), "-o", str(so)], check=True)
+    l = C.CDLL(str(so))
+    l.f1.restype = l.f2.restype = C.c_double
+    l.f1.argtypes = [C.c_int, C.c_double]
+    l.f2.argtypes = [C.c_int, C.c_double, C.c_double]
+    l.d2.argtypes = [C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    return l
+
+
+K = 0.37
+
+
+def _g2(x, y, a=2.0):
+    t = np.sqrt(x**2 + y**2)
+    u = np.where(t < 1.5, np.cos(a*t)*K, np.exp(-t))
+    return u + np.abs(x)*np.arctan2(y, x + 5) - y**3/7
+
+
+def test_translator_matches_numpy():
+    fs = flatten_raytracer(scenes.zoo_numeric(ot))
+    funcs = list(fs.user_funcs) + [("surf2d", _g2, dict(a=1.3)), ("surf2d", lambda x, y: 0.1*np.cos(2*np.pi*x/2), {}),
+                                   ("mask2d", lambda x, y: (x > -1) & (np.hypot(x, y) <= 2.5), {})]
+    lib = _compile_host(userfunc.generate_header(funcs))
+    rng = np.random.default_rng(0)
+    x, y = rng.uniform(-3, 3, 200), rng.uniform(-3, 3, 200)
+    for i, (kind, fn, kw) in enumerate(funcs):
+        if kind == "deriv2d":
+            ex, ey = fn(x, y, **kw)
+            a, b = C.c_double(), C.c_double()
+            for j in range(x.size):
+                lib.d2(i, x[j], y[j], C.byref(a), C.byref(b))
+                assert abs(a.value - ex[j]) <= 1e-15*max(1, abs(ex[j])) and abs(b.value - ey[j]) <= 1e-15*max(1, abs(ey[j]))
+        elif kind.endswith("1d"):
+            ref = np.asarray(fn(np.abs(x), **kw), dtype=np.float64)
+            got = np.array([lib.f1(i, v) for v in np.abs(x)])
+            assert np.allclose(got, ref, rtol=1e-15, atol=0), kind
+        else:
+            ref = np.asarray(fn(x, y, **kw), dtype=np.float64)
+            got = np.array([lib.f2(i, a, b) for a, b in zip(x, y)])
+            assert np.allclose(got, ref, rtol=2e-15, atol=1e-16), kind
+
+
+def test_translator_rejects_unsupported_code():
+    def bad(x, y):
+        return np.fft.fft(x)
+    with pytest.raises(NotImplementedError):
+        userfunc.translate("surf2d", bad, {}, "f")

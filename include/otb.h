@@ -358,6 +358,10 @@ int otb_medium_eval(const OtbMedium* med_h, const double* aux_h, int64_t naux, i
 /* SphericalSurface.sphere_projection (spherical_surface.py:36-97) on (N,3) F-order points. */
 int otb_sphere_projection(const OtbSurface* surf_h, int method, int64_t N, const double* p_d, double* out_d, void* stream);
 
+/* Self-test: the engine's shared-reciprocal division (q_seq) next to the compiler's IEEE division (q_ieee);
+ * the two must be bit-identical (parity contract of the vector normalisations). */
+int otb_selftest_division(int64_t N, const double* a_d, const double* b_d, double* q_seq_d, double* q_ieee_d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,6 +118,7 @@ SYMBOLS = {
                                      _VP, _VP, _VP, _VP, _VP]),
     "otb_medium_eval": (C.c_int, [C.POINTER(OtbMedium), C.POINTER(C.c_double), _I64, _I64, _VP, _VP, _VP]),
     "otb_sphere_projection": (C.c_int, [C.POINTER(OtbSurface), C.c_int, _I64, _VP, _VP, _VP]),
+    "otb_selftest_division": (C.c_int, [_I64, _VP, _VP, _VP, _VP, _VP]),
 }
 
 _lib = None

@@ -129,41 +129,34 @@ int otb_scene_create(const OtbSceneDesc* d, OtbScene** out)
         otb_set_error("scene contains user callables but this engine build has no compiled user functions");
         return OTB_ERR_UNSUPPORTED;
     }
-    size_t o_surf = 0;
-    size_t o_step = o_surf + sizeof(OtbSurface)*d->n_surfaces;
-    size_t o_med = o_step + sizeof(OtbStep)*d->n_steps;
-    size_t o_fil = o_med + sizeof(OtbMedium)*d->n_media;
-    size_t o_aux = (o_fil + sizeof(OtbFilter)*(d->n_filters > 0 ? d->n_filters : 1) + 15)/16*16;
-    size_t total = o_aux + sizeof(double)*(d->n_aux > 0 ? d->n_aux : 1);
-    std::vector<char> host(total, 0);
-    memcpy(host.data() + o_surf, d->surfaces, sizeof(OtbSurface)*d->n_surfaces);
-    memcpy(host.data() + o_step, d->steps, sizeof(OtbStep)*d->n_steps);
-    memcpy(host.data() + o_med, d->media, sizeof(OtbMedium)*d->n_media);
-    if (d->n_filters > 0) memcpy(host.data() + o_fil, d->filters, sizeof(OtbFilter)*d->n_filters);
-    if (d->n_aux > 0) memcpy(host.data() + o_aux, d->aux, sizeof(double)*d->n_aux);
-
+    if (d->n_steps > OTB_MAX_STEPS || d->n_surfaces > OTB_MAX_STEPS || d->n_media > OTB_MAX_MEDIA || d->n_filters > OTB_MAX_FILTERS) {
+        otb_set_error("scene too large for the kernel-parameter scene: at most %d tracing surfaces, %d media, %d filters",
+                      OTB_MAX_STEPS, OTB_MAX_MEDIA, OTB_MAX_FILTERS);
+        return OTB_ERR_UNSUPPORTED;
+    }
     OtbScene* sc = new OtbScene();
     memset(sc, 0, sizeof(*sc));
-    cudaError_t e = cudaMalloc(&sc->blob, total);
-    if (e != cudaSuccess) { delete sc; return otb_cuda_fail(e, "cudaMalloc(scene)"); }
-    e = cudaMemcpy(sc->blob, host.data(), total, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(sc->blob); delete sc; return otb_cuda_fail(e, "cudaMemcpy(scene)"); }
-    sc->blob_bytes = total;
-    char* b = (char*)sc->blob;
-    sc->dev.surfaces = (const OtbSurface*)(b + o_surf);
-    sc->dev.steps = (const OtbStep*)(b + o_step);
-    sc->dev.media = (const OtbMedium*)(b + o_med);
-    sc->dev.filters = (const OtbFilter*)(b + o_fil);
-    sc->dev.aux = (const double*)(b + o_aux);
-    sc->dev.n_surfaces = d->n_surfaces;
-    sc->dev.n_steps = d->n_steps;
-    sc->dev.n_media = d->n_media;
-    sc->dev.n_filters = d->n_filters;
-    sc->dev.no_pol = d->no_pol;
-    sc->dev.medium0 = d->medium0;
-    sc->dev.n_hurb = d->n_hurb;
-    for (int i = 0; i < 6; ++i) sc->dev.outline[i] = d->outline[i];
-    sc->dev.hurb_factor = d->hurb_factor;
+    KScene& k = sc->k;
+    k.n_steps = d->n_steps;
+    k.n_media = d->n_media;
+    k.n_filters = d->n_filters;
+    k.no_pol = d->no_pol;
+    k.medium0 = d->medium0;
+    k.n_hurb = d->n_hurb;
+    for (int i = 0; i < 6; ++i) k.outline[i] = d->outline[i];
+    k.hurb_factor = d->hurb_factor;
+    for (int i = 0; i < d->n_steps; ++i) k.steps[i] = d->steps[i];
+    for (int i = 0; i < d->n_surfaces; ++i) k.surf[i] = otb_ksurface(d->surfaces[i]);
+    for (int i = 0; i < d->n_media; ++i) k.media[i] = d->media[i];
+    for (int i = 0; i < d->n_filters; ++i) k.filters[i] = d->filters[i];
+    const size_t naux = d->n_aux > 0 ? (size_t)d->n_aux : 1;
+    cudaError_t e = cudaMalloc(&sc->aux_d, sizeof(double)*naux);
+    if (e != cudaSuccess) { delete sc; return otb_cuda_fail(e, "cudaMalloc(scene aux)"); }
+    if (d->n_aux > 0) {
+        e = cudaMemcpy(sc->aux_d, d->aux, sizeof(double)*d->n_aux, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(sc->aux_d); delete sc; return otb_cuda_fail(e, "cudaMemcpy(scene aux)"); }
+    }
+    k.aux = sc->aux_d;
     sc->nt = d->n_steps + 1;
     *out = sc;
     return OTB_OK;
@@ -172,7 +165,7 @@ int otb_scene_create(const OtbSceneDesc* d, OtbScene** out)
 int otb_scene_destroy(OtbScene* scene)
 {
     if (!scene) return OTB_OK;
-    cudaFree(scene->blob);
+    cudaFree(scene->aux_d);
     delete scene;
     return OTB_OK;
 }
@@ -186,8 +179,8 @@ int otb_trace_store(const OtbScene* scene, const OtbRays* rays, const OtbRayStor
                       (long long)out->N, out->nt, (long long)rays->N, scene->nt);
         return OTB_ERR_INVALID_ARG;
     }
-    if (!rays->p0_d || !rays->s0_d || !rays->w0_d || !rays->wl_d || (!scene->dev.no_pol && !rays->pol0_d)
-        || !out->p_d || !out->s_d || !out->w_d || !out->n_d || !out->wl_d || (!scene->dev.no_pol && !out->pol_d)) {
+    if (!rays->p0_d || !rays->s0_d || !rays->w0_d || !rays->wl_d || (!scene->k.no_pol && !rays->pol0_d)
+        || !out->p_d || !out->s_d || !out->w_d || !out->n_d || !out->wl_d || (!scene->k.no_pol && !out->pol_d)) {
         otb_set_error("missing ray array");
         return OTB_ERR_INVALID_ARG;
     }
@@ -196,7 +189,7 @@ int otb_trace_store(const OtbScene* scene, const OtbRays* rays, const OtbRayStor
 
 // ---- stand-alone array evaluation ----------------------------------------------------------------
 struct SurfEvalArgs {
-    OtbSurface S;
+    KSurface S;
     const double* aux;
     int64_t N;
 };
@@ -240,7 +233,7 @@ __global__ void medium_kernel(OtbMedium M, const double* aux, int64_t N, const d
     if (i < N) n[i] = medium_n(M, aux, wl[i]);
 }
 
-__global__ void projection_kernel(OtbSurface S, int method, int64_t N, const double* __restrict__ p, double* __restrict__ out)
+__global__ void projection_kernel(KSurface S, int method, int64_t N, const double* __restrict__ p, double* __restrict__ out)
 {
     int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -290,7 +283,7 @@ int otb_surface_find_hit(const OtbSurface* surf_h, const double* aux_h, int64_t 
     if (N <= 0) return OTB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     SurfEvalArgs a;
-    a.S = *surf_h;
+    a.S = otb_ksurface(*surf_h);
     a.N = N;
     double* aux_d;
     if (int rc = upload_aux(aux_h, naux, &aux_d)) return rc;
@@ -313,7 +306,7 @@ int otb_surface_normals(const OtbSurface* surf_h, const double* aux_h, int64_t n
     if (N <= 0) return OTB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     SurfEvalArgs a;
-    a.S = *surf_h;
+    a.S = otb_ksurface(*surf_h);
     a.N = N;
     double* aux_d;
     if (int rc = upload_aux(aux_h, naux, &aux_d)) return rc;
@@ -333,7 +326,7 @@ int otb_surface_values(const OtbSurface* surf_h, const double* aux_h, int64_t na
     if (N <= 0) return OTB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     SurfEvalArgs a;
-    a.S = *surf_h;
+    a.S = otb_ksurface(*surf_h);
     a.N = N;
     double* aux_d;
     if (int rc = upload_aux(aux_h, naux, &aux_d)) return rc;
@@ -369,7 +362,27 @@ int otb_sphere_projection(const OtbSurface* surf_h, int method, int64_t N, const
     if (!surf_h || !p_d || !out_d) { otb_set_error("null argument"); return OTB_ERR_INVALID_ARG; }
     if (method < OTB_PROJ_EQUIDISTANT || method > OTB_PROJ_STEREOGRAPHIC) { otb_set_error("invalid projection"); return OTB_ERR_INVALID_ARG; }
     if (N <= 0) return OTB_OK;
-    projection_kernel<<<(unsigned)((N + 127)/128), 128, 0, (cudaStream_t)stream>>>(*surf_h, method, N, p_d, out_d);
+    projection_kernel<<<(unsigned)((N + 127)/128), 128, 0, (cudaStream_t)stream>>>(otb_ksurface(*surf_h), method, N, p_d, out_d);
+    OTB_CUDA(cudaGetLastError());
+    return OTB_OK;
+}
+
+// self-test hook: q_seq = shared-reciprocal division (otb_common.cuh), q_ieee = the compiler's a/b
+__global__ void div_selftest_kernel(int64_t N, const double* __restrict__ a, const double* __restrict__ b,
+                                    double* __restrict__ q_seq, double* __restrict__ q_ieee)
+{
+    int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double y = rcp_seq(b[i]);
+    q_seq[i] = div_seq(a[i], b[i], y);
+    q_ieee[i] = a[i]/b[i];
+}
+
+int otb_selftest_division(int64_t N, const double* a_d, const double* b_d, double* q_seq_d, double* q_ieee_d, void* stream)
+{
+    if (!a_d || !b_d || !q_seq_d || !q_ieee_d) { otb_set_error("null argument"); return OTB_ERR_INVALID_ARG; }
+    if (N <= 0) return OTB_OK;
+    div_selftest_kernel<<<(unsigned)((N + 255)/256), 256, 0, (cudaStream_t)stream>>>(N, a_d, b_d, q_seq_d, q_ieee_d);
     OTB_CUDA(cudaGetLastError());
     return OTB_OK;
 }

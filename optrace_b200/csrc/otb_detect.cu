@@ -31,7 +31,9 @@ __device__ __forceinline__ void atomic_max_d(double* addr, double v)
 
 struct DetArgs {
     OtbRayStore st;
-    OtbDetector det;
+    KSurface surf;
+    int projection, has_extent;
+    double extent[4];
     int64_t begin, end;
     double* hx;
     double* hy;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(128) detector_hits_kernel(const DetArgs a)
     const int64_t Nnt = N*(int64_t)nt;
     const double* __restrict__ P = a.st.p_d;
     const float* __restrict__ Wt = a.st.w_d;
-    const OtbSurface& S = a.det.surface;
+    const KSurface& S = a.surf;
     const int64_t ray = a.begin + (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
     const bool valid = ray < a.end;
 
@@ -93,10 +95,10 @@ __global__ void __launch_bounds__(128) detector_hits_kernel(const DetArgs a)
             if (h.hit && w > 0.0f) {
                 X = h.p.x;
                 Y = h.p.y;
-                sphere_project(S, a.det.projection, X, Y, h.p.z);
+                sphere_project(S, a.projection, X, Y, h.p.z);
                 ok = true;
-                if (a.det.has_extent) {
-                    const double* e = a.det.extent;
+                if (a.has_extent) {
+                    const double* e = a.extent;
                     ok = (e[0] <= X) && (X <= e[1]) && (e[2] <= Y) && (Y <= e[3]);
                 }
             }
@@ -194,7 +196,10 @@ int otb_detector_hits(const OtbRayStore* store, int64_t ray_begin, int64_t ray_e
     cudaStream_t st = (cudaStream_t)stream;
     DetArgs a;
     a.st = *store;
-    a.det = *det_h;
+    a.surf = otb_ksurface(det_h->surface);
+    a.projection = det_h->projection;
+    a.has_extent = det_h->has_extent;
+    for (int i = 0; i < 4; ++i) a.extent[i] = det_h->extent[i];
     a.begin = ray_begin;
     a.end = ray_end;
     a.hx = hx_d; a.hy = hy_d; a.hw = hw_d;

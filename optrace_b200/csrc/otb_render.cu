@@ -15,7 +15,9 @@
 #define OTB_MAX_DET 8
 
 struct RenderDet {
-    OtbDetector det;
+    KSurface surf;
+    int projection, has_extent;
+    double extent[4];
     BinGrid grid;
     double* img;
     int* cnt;
@@ -23,7 +25,7 @@ struct RenderDet {
 };
 
 struct RenderArgs {
-    DevScene sc;
+    KScene sc;
     OtbRays in;
     const RenderDet* dets;
     int n_det;
@@ -63,10 +65,10 @@ __device__ __forceinline__ void atomic_max_dd(double* addr, double v)
 
 template <bool POL>
 __global__ void __launch_bounds__(OTB_RENDER_THREADS)
-trace_render_kernel(const RenderArgs a)
+trace_render_kernel(const __grid_constant__ RenderArgs a)
 {
     extern __shared__ int smsgs[];
-    const DevScene& sc = a.sc;
+    const KScene& sc = a.sc;
     const int nt = a.nt;
     const int64_t N = a.in.N;
     const int NDET = a.n_det;
@@ -99,7 +101,7 @@ trace_render_kernel(const RenderArgs a)
 
         DetState ds[OTB_MAX_DET];
         for (int d = 0; d < NDET; ++d) {
-            const OtbSurface& D = a.dets[d].det.surface;
+            const KSurface& D = a.dets[d].surf;
             const bool bmin = r.p.z >= D.z_min, bmax = r.p.z >= D.z_max;
             ds[d].X = ds[d].Y = 0.0;
             ds[d].w = 0.0f;
@@ -126,15 +128,11 @@ trace_render_kernel(const RenderArgs a)
             const float w_i = r.w;
             StepFlags fl;
             trace_step<POL>(sc, st, r, fl, za, zb, a.status);
-            book(smsgs, OTB_MSG_ILL_COND*nt + i + 1, valid && fl.ill);
-            book(smsgs, OTB_MSG_ABSORB_MISSING*nt + i + 1, valid && fl.absorb_missing);
-            book(smsgs, OTB_MSG_TIR*nt + i, valid && fl.tir);
-            book(smsgs, OTB_MSG_OUTLINE*nt + i, valid && fl.outline);
-            if (st.hurb) book(smsgs, OTB_MSG_HURB_NEG*nt + i + 1, valid && fl.hurb_neg);
+            book_step(smsgs, nt, i, valid, fl);
 
             // detector walk over section i = (p_i -> r.p)
             for (int d = 0; d < NDET; ++d) {
-                const OtbSurface& D = a.dets[d].det.surface;
+                const KSurface& D = a.dets[d].surf;
                 const bool bmin = r.p.z >= D.z_min, bmax = r.p.z >= D.z_max;
                 ds[d].all_start = ds[d].all_start && (bmin && bmax);
                 ds[d].all_noreach = ds[d].all_noreach && (!bmin && !bmax);
@@ -146,7 +144,7 @@ trace_render_kernel(const RenderArgs a)
                         ds[d].finished = true;
                         if (h.hit && w_i > 0.0f) {
                             double X = h.p.x, Y = h.p.y;
-                            sphere_project(D, a.dets[d].det.projection, X, Y, h.p.z);
+                            sphere_project(D, a.dets[d].projection, X, Y, h.p.z);
                             ds[d].X = X;
                             ds[d].Y = Y;
                             ds[d].w = w_i;
@@ -161,8 +159,8 @@ trace_render_kernel(const RenderArgs a)
         for (int d = 0; d < NDET; ++d) {
             bool ok = valid && ds[d].ok && !(ds[d].all_start || ds[d].all_noreach);
             const RenderDet& rd = a.dets[d];
-            if (ok && rd.det.has_extent) {
-                const double* e = rd.det.extent;
+            if (ok && rd.has_extent) {
+                const double* e = rd.extent;
                 ok = (e[0] <= ds[d].X) && (ds[d].X <= e[1]) && (e[2] <= ds[d].Y) && (ds[d].Y <= e[3]);
             }
             if (a.mode == 0) {
@@ -222,7 +220,10 @@ extern "C" int otb_trace_render(const OtbScene* scene, const OtbRays* rays, int 
             otb_set_error("Function/Data surfaces are not supported as detector surfaces (detector.py:37-41)");
             return OTB_ERR_UNSUPPORTED;
         }
-        hd[d].det = dets_h[d];
+        hd[d].surf = otb_ksurface(dets_h[d].surface);
+        hd[d].projection = dets_h[d].projection;
+        hd[d].has_extent = dets_h[d].has_extent;
+        for (int q = 0; q < 4; ++q) hd[d].extent[q] = dets_h[d].extent[q];
         if (mode == 0) {
             const double* e = extents_h + 4*d;
             if (Nx_h[d] <= 0 || Ny_h[d] <= 0 || !(e[1] > e[0]) || !(e[3] > e[2]) || !img_d[d]) {
@@ -240,7 +241,7 @@ extern "C" int otb_trace_render(const OtbScene* scene, const OtbRays* rays, int 
     OTB_CUDA(cudaMalloc(&dd, sizeof(RenderDet)*n_det));
     OTB_CUDA(cudaMemcpyAsync(dd, hd, sizeof(RenderDet)*n_det, cudaMemcpyHostToDevice, st));
     RenderArgs a;
-    a.sc = scene->dev;
+    a.sc = scene->k;
     a.in = *rays;
     a.dets = dd;
     a.n_det = n_det;
@@ -253,7 +254,7 @@ extern "C" int otb_trace_render(const OtbScene* scene, const OtbRays* rays, int 
     int64_t blocks_needed = (N + OTB_RENDER_THREADS - 1)/OTB_RENDER_THREADS, cap = (int64_t)otb_sm_count()*16;
     int blocks = (int)(blocks_needed < cap ? blocks_needed : cap);
     size_t smem = sizeof(int)*OTB_NMSG*scene->nt;
-    if (scene->dev.no_pol) launch_render<false>(blocks, smem, st, a);
+    if (scene->k.no_pol) launch_render<false>(blocks, smem, st, a);
     else launch_render<true>(blocks, smem, st, a);
     cudaError_t e = cudaGetLastError();
     OTB_CUDA(cudaStreamSynchronize(st));

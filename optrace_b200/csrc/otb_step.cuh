@@ -67,7 +67,7 @@ __device__ __forceinline__ bool outline_clip(const double* __restrict__ o, const
 }
 
 // HURB geometry: RingSurface.hurb_props (ring_surface.py:88-121), SlitSurface.hurb_props (slit_surface.py:65-87)
-__device__ __forceinline__ void hurb_props(const OtbSurface& S, double x, double y, double& a_, double& b_, V3& b, bool& inside)
+__device__ __forceinline__ void hurb_props(const KSurface& S, double x, double y, double& a_, double& b_, V3& b, bool& inside)
 {
     const double dx = x - S.pos[0], dy = y - S.pos[1];
     if (S.kind == OTB_SURF_RING) {
@@ -91,10 +91,10 @@ __device__ __forceinline__ void hurb_props(const OtbSurface& S, double x, double
 // One sequential step.  On entry `r` holds section i, on exit section i+1 (p, w, pol, n) and the new direction.
 // za, zb: standard normal deviates for HURB (only read when the step bends rays).
 template <bool POL>
-__device__ __forceinline__ void trace_step(const DevScene& sc, const OtbStep& st, RayState& r, StepFlags& fl,
+__device__ __forceinline__ void trace_step(const KScene& sc, const OtbStep& st, RayState& r, StepFlags& fl,
                                            double za, double zb, int* status)
 {
-    const OtbSurface& S = sc.surfaces[st.surface];
+    const KSurface& S = sc.surf[st.surface];
     const double* __restrict__ aux = sc.aux;
     fl.ill = fl.absorb_missing = fl.tir = fl.outline = fl.hurb_neg = false;
 
@@ -218,9 +218,23 @@ __device__ __forceinline__ void trace_step(const DevScene& sc, const OtbStep& st
     }
 }
 
-// warp-aggregated message booking: one shared-memory atomic per warp and message type
+// warp-aggregated message booking: one shared-memory atomic per warp and message type; the common case
+// (no message in the whole warp) costs one vote
 __device__ __forceinline__ void book(int* smsgs, int slot, bool pred)
 {
     unsigned b = __ballot_sync(0xffffffffu, pred);
     if (b && (threadIdx.x & 31) == 0) atomicAdd(&smsgs[slot], __popc(b));
+}
+
+// section indices as in raytracer.py:318, 323, 486 (i+1) vs :718, 826 (i)
+__device__ __forceinline__ void book_step(int* smsgs, int nt, int i, bool valid, const StepFlags& fl)
+{
+    const bool any = valid && (fl.ill || fl.absorb_missing || fl.tir || fl.outline || fl.hurb_neg);
+    if (__any_sync(0xffffffffu, any)) {
+        book(smsgs, OTB_MSG_ILL_COND*nt + i + 1, valid && fl.ill);
+        book(smsgs, OTB_MSG_ABSORB_MISSING*nt + i + 1, valid && fl.absorb_missing);
+        book(smsgs, OTB_MSG_TIR*nt + i, valid && fl.tir);
+        book(smsgs, OTB_MSG_OUTLINE*nt + i, valid && fl.outline);
+        book(smsgs, OTB_MSG_HURB_NEG*nt + i + 1, valid && fl.hurb_neg);
+    }
 }

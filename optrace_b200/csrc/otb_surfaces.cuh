@@ -11,7 +11,7 @@ struct HitResult {
 };
 
 // Surface._rotate_rc (surface.py:427-434) with host-precomputed cos/sin
-__device__ __forceinline__ void rot_rc(const OtbSurface& S, int cslot, double x, double y, double& xr, double& yr)
+__device__ __forceinline__ void rot_rc(const KSurface& S, int cslot, double x, double y, double& xr, double& yr)
 {
     if (S.flags & OTB_SF_ROTATED) {
         double c = S.par[cslot], s = S.par[cslot + 1];
@@ -124,7 +124,7 @@ __device__ __forceinline__ double polyval(const double* __restrict__ c, int n, d
 // RectangularSurface.mask (rectangular_surface.py:100-112), SlitSurface.mask (slit_surface.py:89-102),
 // FunctionSurface2D.mask (function_surface_2d.py:158-191).  Absolute coordinates.
 // ------------------------------------------------------------------------------------------------
-__device__ inline bool surf_mask(const OtbSurface& S, double x, double y)
+__device__ inline bool surf_mask(const KSurface& S, double x, double y)
 {
     const double x0 = S.pos[0], y0 = S.pos[1];
     switch (S.kind) {
@@ -173,7 +173,7 @@ __device__ inline bool surf_mask(const OtbSurface& S, double x, double y)
 // (conic_surface.py:57-68, tilted_surface.py:61-74, aspheric_surface.py:51-66,
 //  function_surface_2d.py:133-156, data_surface_2d.py:130-153)
 // ------------------------------------------------------------------------------------------------
-__device__ inline double surf_values_rel(const OtbSurface& S, const double* __restrict__ aux, double x, double y)
+__device__ inline double surf_values_rel(const KSurface& S, const double* __restrict__ aux, double x, double y)
 {
     switch (S.kind) {
     case OTB_SURF_CONIC: {
@@ -218,7 +218,7 @@ __device__ inline double surf_values_rel(const OtbSurface& S, const double* __re
 }
 
 // Surface.values (surface.py:137-164): absolute height with the radially continued edge
-__device__ inline double surf_values(const OtbSurface& S, const double* __restrict__ aux, double x, double y)
+__device__ inline double surf_values(const KSurface& S, const double* __restrict__ aux, double x, double y)
 {
     if (S.flags & OTB_SF_FLAT) return S.z_max;
     if (surf_mask(S, x, y)) return S.pos[2] + surf_values_rel(S, aux, x - S.pos[0], y - S.pos[1]);
@@ -233,7 +233,7 @@ __device__ inline double surf_values(const OtbSurface& S, const double* __restri
 // TiltedSurface.normals (tilted_surface.py:76-89), FunctionSurface2D.normals
 // (function_surface_2d.py:193-253), DataSurface2D.normals (data_surface_2d.py:155-196)
 // ------------------------------------------------------------------------------------------------
-__device__ inline V3 surf_normal(const OtbSurface& S, const double* __restrict__ aux, double x, double y)
+__device__ inline V3 surf_normal(const KSurface& S, const double* __restrict__ aux, double x, double y)
 {
     const int k = S.kind;
     if ((S.flags & OTB_SF_FLAT) && k != OTB_SURF_TILTED) return v3(0.0, 0.0, 1.0);
@@ -302,7 +302,7 @@ __device__ inline V3 surf_normal(const OtbSurface& S, const double* __restrict__
 // intersection
 // ------------------------------------------------------------------------------------------------
 // Surface._find_hit_handle_abnormal (surface.py:436-479)
-__device__ inline void handle_abnormal(const OtbSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, HitResult& h)
+__device__ inline void handle_abnormal(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, HitResult& h)
 {
     double zs = surf_values(S, aux, h.p.x, h.p.y);
     bool dev = fabs(h.p.z - zs) > OTB_C_EPS;
@@ -322,7 +322,7 @@ __device__ inline void handle_abnormal(const OtbSurface& S, const double* __rest
 
 // Surface.find_hit (surface.py:307-414): plane for flat surfaces, Illinois regula falsi otherwise.
 // `status` receives OTB_STATUS_TIMEOUT when the 200-iteration limit is reached (surface.py:403).
-__device__ inline HitResult find_hit_numeric(const OtbSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
+__device__ inline HitResult find_hit_numeric(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
 {
     HitResult h;
     h.ill = false;
@@ -373,7 +373,7 @@ __device__ inline HitResult find_hit_numeric(const OtbSurface& S, const double* 
 }
 
 // ConicSurface.find_hit (conic_surface.py:126-203)
-__device__ inline HitResult find_hit_conic(const OtbSurface& S, const V3& p, const V3& s)
+__device__ inline HitResult find_hit_conic(const KSurface& S, const V3& p, const V3& s)
 {
     HitResult h;
     h.ill = false;
@@ -383,7 +383,9 @@ __device__ inline HitResult find_hit_conic(const OtbSurface& S, const V3& p, con
     const double B = s.x*ox + s.y*oy + s.z*(oz*kp1 - S.par[OTB_P_INVRHO]);
     const double Cc = oy*oy + ox*ox + oz*(oz*kp1 - S.par[OTB_P_TWOINVRHO]);
     const double D = sqrt(B*B - Cc*A);
-    const double t1 = (-B - D)/A, t2 = (-B + D)/A;
+    // sphere: A is the literal 1.0 and x/1.0 == x exactly, so the two divisions are skipped
+    const bool unitA = (A == 1.0);
+    const double t1 = unitA ? (-B - D) : (-B - D)/A, t2 = unitA ? (-B + D) : (-B + D)/A;
     const double z = p.z;
     const double z1 = z + s.z*t1, z2 = z + s.z*t2;
     const double z_min = S.z_min - OTB_N_EPS, z_max = S.z_max + OTB_N_EPS;
@@ -411,7 +413,7 @@ __device__ inline HitResult find_hit_conic(const OtbSurface& S, const V3& p, con
 }
 
 // TiltedSurface.find_hit (tilted_surface.py:91-123)
-__device__ inline HitResult find_hit_tilted(const OtbSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
+__device__ inline HitResult find_hit_tilted(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
 {
     HitResult h;
     const V3 n = v3(S.par[OTB_P_NX], S.par[OTB_P_NY], S.par[OTB_P_NZ]);
@@ -427,7 +429,7 @@ __device__ inline HitResult find_hit_tilted(const OtbSurface& S, const double* _
     return h;
 }
 
-__device__ inline HitResult surf_find_hit(const OtbSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
+__device__ inline HitResult surf_find_hit(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
 {
     switch (S.kind) {
     case OTB_SURF_CONIC: return find_hit_conic(S, p, s);
@@ -437,7 +439,7 @@ __device__ inline HitResult surf_find_hit(const OtbSurface& S, const double* __r
 }
 
 // SphericalSurface.sphere_projection (spherical_surface.py:36-97), in place on (x, y) given z
-__device__ __forceinline__ void sphere_project(const OtbSurface& S, int method, double& x, double& y, double z)
+__device__ __forceinline__ void sphere_project(const KSurface& S, int method, double& x, double& y, double z)
 {
     if (method == OTB_PROJ_NONE || method == OTB_PROJ_ORTHOGRAPHIC) return;
     const double R = S.par[OTB_P_R];

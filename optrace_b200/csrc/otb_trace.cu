@@ -2,115 +2,112 @@
 // in ONE launch.  Thread = ray, ray state in registers, every section written once as coalesced SoA planes
 // in the byte layout of RayStorage (ray_storage.py:80-90).  No tensor cores: the path is not a contraction.
 //
+// The scene (steps, surfaces, media, filters) is a __grid_constant__ kernel parameter: warp-uniform values come
+// from the constant bank, not from global memory.
 // HBM traffic per ray: read 68 B (injected bundle) ; write nt*48 + 24 B (pol) or nt*36 + 24 B (no_pol).
 #include "otb_step.cuh"
 
 #define OTB_TRACE_THREADS 128
 
 struct TraceArgs {
-    DevScene sc;
+    KScene sc;
     OtbRays in;
     OtbRayStore out;
     unsigned long long* msgs;   // [OTB_NMSG * nt]
     int* status;
 };
 
-
 template <bool POL>
 __global__ void __launch_bounds__(OTB_TRACE_THREADS)
-trace_store_kernel(const TraceArgs a)
+trace_store_kernel(const __grid_constant__ TraceArgs a)
 {
     extern __shared__ int smsgs[];      // [OTB_NMSG * nt]
-    const DevScene& sc = a.sc;
+    const KScene& sc = a.sc;
     const int nt = a.out.nt;
     const int64_t N = a.out.N;
     for (int i = threadIdx.x; i < OTB_NMSG*nt; i += blockDim.x) smsgs[i] = 0;
     __syncthreads();
 
-    double* __restrict__ P = a.out.p_d;
-    float* __restrict__ Wt = a.out.w_d;
-    float* __restrict__ PL = a.out.pol_d;
-    double* __restrict__ NS = a.out.n_d;
     const int64_t Nnt = N*(int64_t)nt;
 
     for (int64_t base = (int64_t)blockIdx.x*blockDim.x; base < N; base += (int64_t)gridDim.x*blockDim.x) {
         const int64_t ray = base + threadIdx.x;
         const bool valid = ray < N;
+        const int64_t rr = valid ? ray : 0;          // clamp so that every lane addresses valid memory
         RayState r;
-        if (valid) {
-            r.p = v3(a.in.p0_d[ray], a.in.p0_d[ray + N], a.in.p0_d[ray + 2*N]);
-            r.s = v3(a.in.s0_d[ray], a.in.s0_d[ray + N], a.in.s0_d[ray + 2*N]);
-            r.w = a.in.w0_d[ray];
-            r.wl = a.in.wl_d[ray];
-            if (POL) {
-                r.pol[0] = a.in.pol0_d[ray];
-                r.pol[1] = a.in.pol0_d[ray + N];
-                r.pol[2] = a.in.pol0_d[ray + 2*N];
-            }
+        r.p = v3(a.in.p0_d[rr], a.in.p0_d[rr + N], a.in.p0_d[rr + 2*N]);
+        r.s = v3(a.in.s0_d[rr], a.in.s0_d[rr + N], a.in.s0_d[rr + 2*N]);
+        r.w = valid ? a.in.w0_d[rr] : 0.0f;
+        r.wl = a.in.wl_d[rr];
+        if (POL) {
+            r.pol[0] = a.in.pol0_d[rr];
+            r.pol[1] = a.in.pol0_d[rr + N];
+            r.pol[2] = a.in.pol0_d[rr + 2*N];
         } else {
-            r.p = v3(0, 0, 0);
-            r.s = v3(0, 0, 1);
-            r.w = 0.0f;
-            r.wl = 550.0f;
             r.pol[0] = r.pol[1] = r.pol[2] = 0.0f;
         }
-        r.n = medium_n(sc.media[sc.medium0], sc.aux, r.wl);
+        r.n = medium_n(sc.media[sc.medium0], sc.aux, (double)r.wl);
         if (valid && r.n < 1.0) atomicOr(a.status, OTB_STATUS_NBELOW1);
 
+        // running plane pointers: one add per plane and section instead of 64-bit index arithmetic
+        double* pp = a.out.p_d + rr;
+        float* pw = a.out.w_d + rr;
+        double* pn = a.out.n_d + rr;
+        float* ppol = POL ? a.out.pol_d + rr : nullptr;
+
         if (valid) {
-            __stcs(&P[ray], r.p.x);
-            __stcs(&P[ray + Nnt], r.p.y);
-            __stcs(&P[ray + 2*Nnt], r.p.z);
-            __stcs(&Wt[ray], r.w);
-            __stcs(&NS[ray], r.n);
-            __stcs(&a.out.wl_d[ray], r.wl);
+            __stcs(pp, r.p.x);
+            __stcs(pp + Nnt, r.p.y);
+            __stcs(pp + 2*Nnt, r.p.z);
+            __stcs(pw, r.w);
+            __stcs(pn, r.n);
+            __stcs(&a.out.wl_d[rr], r.wl);
             if (POL) {
-                __stcs(&PL[ray], r.pol[0]);
-                __stcs(&PL[ray + Nnt], r.pol[1]);
-                __stcs(&PL[ray + 2*Nnt], r.pol[2]);
+                __stcs(ppol, r.pol[0]);
+                __stcs(ppol + Nnt, r.pol[1]);
+                __stcs(ppol + 2*Nnt, r.pol[2]);
             }
         }
 
         for (int i = 0; i < sc.n_steps; ++i) {
             const OtbStep& st = sc.steps[i];
             double za = 0.0, zb = 0.0;
-            if (st.hurb && valid) {
+            if (st.hurb) {
                 if (a.in.hurb_z_d) {
-                    za = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 0)*N + ray];
-                    zb = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 1)*N + ray];
+                    za = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 0)*N + rr];
+                    zb = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 1)*N + rr];
                 } else {
-                    Philox4 rnd = philox4x32_10((uint64_t)(a.in.ray_offset + ray), 0x48555242u, (uint32_t)st.hurb_slot, a.in.seed);
+                    Philox4 rnd = philox4x32_10((uint64_t)(a.in.ray_offset + rr), 0x48555242u, (uint32_t)st.hurb_slot, a.in.seed);
                     normal2(rnd, za, zb);
                 }
             }
             StepFlags fl;
             trace_step<POL>(sc, st, r, fl, za, zb, a.status);
+            book_step(smsgs, nt, i, valid, fl);
 
-            // message booking (section indices as in raytracer.py:318, 323, 486 vs :718, 826)
-            book(smsgs, OTB_MSG_ILL_COND*nt + i + 1, valid && fl.ill);
-            book(smsgs, OTB_MSG_ABSORB_MISSING*nt + i + 1, valid && fl.absorb_missing);
-            book(smsgs, OTB_MSG_TIR*nt + i, valid && fl.tir);
-            book(smsgs, OTB_MSG_OUTLINE*nt + i, valid && fl.outline);
-            if (st.hurb) book(smsgs, OTB_MSG_HURB_NEG*nt + i + 1, valid && fl.hurb_neg);
-
+            pp += N;
+            pw += N;
+            pn += N;
             if (valid) {
-                const int64_t o = ray + N*(int64_t)(i + 1);
-                __stcs(&P[o], r.p.x);
-                __stcs(&P[o + Nnt], r.p.y);
-                __stcs(&P[o + 2*Nnt], r.p.z);
-                __stcs(&Wt[o], r.w);
-                __stcs(&NS[o], r.n);
-                if (POL) {
-                    __stcs(&PL[o], r.pol[0]);
-                    __stcs(&PL[o + Nnt], r.pol[1]);
-                    __stcs(&PL[o + 2*Nnt], r.pol[2]);
+                __stcs(pp, r.p.x);
+                __stcs(pp + Nnt, r.p.y);
+                __stcs(pp + 2*Nnt, r.p.z);
+                __stcs(pw, r.w);
+                __stcs(pn, r.n);
+            }
+            if (POL) {
+                ppol += N;
+                if (valid) {
+                    __stcs(ppol, r.pol[0]);
+                    __stcs(ppol + Nnt, r.pol[1]);
+                    __stcs(ppol + 2*Nnt, r.pol[2]);
                 }
             }
         }
         if (valid) {
-            __stcs(&a.out.s_d[ray], r.s.x);
-            __stcs(&a.out.s_d[ray + N], r.s.y);
-            __stcs(&a.out.s_d[ray + 2*N], r.s.z);
+            __stcs(&a.out.s_d[rr], r.s.x);
+            __stcs(&a.out.s_d[rr + N], r.s.y);
+            __stcs(&a.out.s_d[rr + 2*N], r.s.z);
         }
     }
 
@@ -123,7 +120,7 @@ int otb_launch_trace_store(const OtbScene* scene, const OtbRays* rays, const Otb
                            int64_t* msgs_d, int32_t* status_d, cudaStream_t stream, int sm_count)
 {
     TraceArgs a;
-    a.sc = scene->dev;
+    a.sc = scene->k;
     a.in = *rays;
     a.out = *out;
     a.msgs = (unsigned long long*)msgs_d;
@@ -136,7 +133,7 @@ int otb_launch_trace_store(const OtbScene* scene, const OtbRays* rays, const Otb
     int64_t cap = (int64_t)sm_count*16;
     int blocks = (int)(blocks_needed < cap ? blocks_needed : cap);
     size_t smem = sizeof(int)*OTB_NMSG*out->nt;
-    if (scene->dev.no_pol)
+    if (scene->k.no_pol)
         trace_store_kernel<false><<<blocks, threads, smem, stream>>>(a);
     else
         trace_store_kernel<true><<<blocks, threads, smem, stream>>>(a);

@@ -241,3 +241,23 @@ def test_fused_render_matches_reference_fixture(ot):
             assert 0 <= missing <= 4, (name, v, missing)
             tot = float(g[k + "vals"][:, 3].sum())
             assert abs(float(d[:, :, 3].sum()) - tot) <= 3e-7*tot + missing*float(g[k + "w"].max()), (name, v)
+
+
+def test_shared_reciprocal_division_is_exact(ot):
+    """the hoisted-reciprocal division used for vector normalisation equals IEEE division bit for bit"""
+    import ctypes as C
+    import torch
+    from optrace_b200 import engine, _cabi
+    lib = engine.ensure_init()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    N = 1 << 24
+    for scale in (1.0, 1e-3, 1e6, 1e-150, 1e150):
+        a = (torch.rand(N, dtype=torch.float64, device="cuda", generator=g)*2 - 1)*scale
+        b = (torch.rand(N, dtype=torch.float64, device="cuda", generator=g) + 1e-6)*3.7
+        a[:8] = torch.tensor([0.0, -0.0, float("nan"), float("inf"), 1.0, -1.0, 5e-324, 1e308], dtype=torch.float64)
+        b[8:12] = torch.tensor([0.0, float("inf"), float("nan"), 1e-310], dtype=torch.float64)
+        qs, qi = torch.empty_like(a), torch.empty_like(a)
+        _cabi.check(lib.otb_selftest_division(N, engine.dptr(a), engine.dptr(b), engine.dptr(qs), engine.dptr(qi),
+                                              engine.stream_ptr()), lib)
+        same = (qs.view(torch.int64) == qi.view(torch.int64)) | (torch.isnan(qs) & torch.isnan(qi))
+        assert bool(same.all()), (scale, int((~same).sum()))

@@ -13,7 +13,7 @@ NPAR = 20
 NMSG = 5
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "csrc" / "libotb.so"
+LIB_PATH = pathlib.Path(os.environ.get("OTB_LIB", _HERE / "csrc" / "libotb.so"))   # OTB_LIB: experiment builds
 
 
 class OtbSurface(C.Structure):

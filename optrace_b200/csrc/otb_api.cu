@@ -158,6 +158,12 @@ int otb_scene_create(const OtbSceneDesc* d, OtbScene** out)
     }
     k.aux = sc->aux_d;
     sc->nt = d->n_steps + 1;
+    sc->caps = OTB_CAPS_LENS;
+    for (int i = 0; i < d->n_surfaces; ++i) {
+        const int kd = d->surfaces[i].kind;
+        if (kd == OTB_SURF_TILTED || kd == OTB_SURF_ASPHERE || kd == OTB_SURF_FUNC || kd == OTB_SURF_DATA) sc->caps = OTB_CAPS_FULL;
+    }
+    for (int i = 0; i < d->n_steps; ++i) if (d->steps[i].hurb) sc->caps = OTB_CAPS_FULL;
     *out = sc;
     return OTB_OK;
 }
@@ -200,7 +206,7 @@ __global__ void find_hit_kernel(SurfEvalArgs a, const double* __restrict__ p, co
     int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= a.N) return;
     V3 P = v3(p[i], p[i + a.N], p[i + 2*a.N]), Sd = v3(s[i], s[i + a.N], s[i + 2*a.N]);
-    HitResult h = surf_find_hit(a.S, a.aux, P, Sd, status);
+    HitResult h = surf_find_hit<OTB_CAPS_FULL>(a.S, a.aux, P, Sd, status);
     ph[i] = h.p.x;
     ph[i + a.N] = h.p.y;
     ph[i + 2*a.N] = h.p.z;
@@ -212,7 +218,7 @@ __global__ void normals_kernel(SurfEvalArgs a, const double* __restrict__ x, con
 {
     int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= a.N) return;
-    V3 v = surf_normal(a.S, a.aux, x[i], y[i]);
+    V3 v = surf_normal<OTB_CAPS_FULL>(a.S, a.aux, x[i], y[i]);
     n[i] = v.x;
     n[i + a.N] = v.y;
     n[i + 2*a.N] = v.z;
@@ -223,7 +229,7 @@ __global__ void values_kernel(SurfEvalArgs a, const double* __restrict__ x, cons
 {
     int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= a.N) return;
-    if (z) z[i] = surf_values(a.S, a.aux, x[i], y[i]);
+    if (z) z[i] = surf_values<OTB_CAPS_FULL>(a.S, a.aux, x[i], y[i]);
     if (m) m[i] = surf_mask(a.S, x[i], y[i]);
 }
 

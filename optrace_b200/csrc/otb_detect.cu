@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) detector_hits_kernel(const DetArgs a)
                     w = 0.0f;
                     break;
                 }
-                h = surf_find_hit(S, nullptr, p, s, a.status);
+                h = surf_find_hit<OTB_CAPS_FULL>(S, nullptr, p, s, a.status);
                 ill = ill || h.ill;
                 const double p2z = P[ray + N*(int64_t)sec + 2*Nnt];
                 more = h.p.z > p2z + OTB_C_EPS;      // hit behind the next stored point -> try next section

@@ -63,8 +63,8 @@ __device__ __forceinline__ void atomic_max_dd(double* addr, double v)
     } while (assumed != old);
 }
 
-template <bool POL>
-__global__ void __launch_bounds__(OTB_RENDER_THREADS)
+template <bool POL, int CAPS>
+__global__ void __launch_bounds__(OTB_RENDER_THREADS, (CAPS == OTB_CAPS_LENS ? 4 : 3))
 trace_render_kernel(const __grid_constant__ RenderArgs a)
 {
     extern __shared__ int smsgs[];
@@ -115,7 +115,7 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
         for (int i = 0; i < sc.n_steps; ++i) {
             const OtbStep& st = sc.steps[i];
             double za = 0.0, zb = 0.0;
-            if (st.hurb && valid) {
+            if (CAPS == OTB_CAPS_FULL && st.hurb && valid) {
                 if (a.in.hurb_z_d) {
                     za = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 0)*N + ray];
                     zb = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 1)*N + ray];
@@ -127,7 +127,7 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
             const V3 p_i = r.p;
             const float w_i = r.w;
             StepFlags fl;
-            trace_step<POL>(sc, st, r, fl, za, zb, a.status);
+            trace_step<POL, CAPS>(sc, st, r, fl, za, zb, a.status);
             book_step(smsgs, nt, i, valid, fl);
 
             // detector walk over section i = (p_i -> r.p)
@@ -139,7 +139,7 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
                 if (!ds[d].started && bmin) ds[d].started = true;     // section before the first point behind z_min
                 if (valid && ds[d].started && !ds[d].finished) {
                     const V3 sd = unit3(v3(r.p.x - p_i.x, r.p.y - p_i.y, r.p.z - p_i.z));
-                    HitResult h = surf_find_hit(D, nullptr, p_i, sd, a.status);
+                    HitResult h = surf_find_hit<CAPS>(D, nullptr, p_i, sd, a.status);
                     if (!(h.p.z > r.p.z + OTB_C_EPS)) {
                         ds[d].finished = true;
                         if (h.hit && w_i > 0.0f) {
@@ -191,9 +191,10 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
 }
 
 template <bool POL>
-static void launch_render(int blocks, size_t smem, cudaStream_t stream, const RenderArgs& a)
+static void launch_render(bool lean, int blocks, size_t smem, cudaStream_t stream, const RenderArgs& a)
 {
-    trace_render_kernel<POL><<<blocks, OTB_RENDER_THREADS, smem, stream>>>(a);
+    if (lean) trace_render_kernel<POL, OTB_CAPS_LENS><<<blocks, OTB_RENDER_THREADS, smem, stream>>>(a);
+    else trace_render_kernel<POL, OTB_CAPS_FULL><<<blocks, OTB_RENDER_THREADS, smem, stream>>>(a);
 }
 
 int otb_observer_table(const double** out);
@@ -254,8 +255,10 @@ extern "C" int otb_trace_render(const OtbScene* scene, const OtbRays* rays, int 
     int64_t blocks_needed = (N + OTB_RENDER_THREADS - 1)/OTB_RENDER_THREADS, cap = (int64_t)otb_sm_count()*16;
     int blocks = (int)(blocks_needed < cap ? blocks_needed : cap);
     size_t smem = sizeof(int)*OTB_NMSG*scene->nt;
-    if (scene->k.no_pol) launch_render<false>(blocks, smem, st, a);
-    else launch_render<true>(blocks, smem, st, a);
+    bool lean = scene->caps == OTB_CAPS_LENS;
+    for (int d = 0; d < n_det; ++d) if (dets_h[d].surface.kind == OTB_SURF_TILTED) lean = false;
+    if (scene->k.no_pol) launch_render<false>(lean, blocks, smem, st, a);
+    else launch_render<true>(lean, blocks, smem, st, a);
     cudaError_t e = cudaGetLastError();
     OTB_CUDA(cudaStreamSynchronize(st));
     cudaFree(dd);

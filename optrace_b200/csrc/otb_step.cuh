@@ -90,7 +90,7 @@ __device__ __forceinline__ void hurb_props(const KSurface& S, double x, double y
 
 // One sequential step.  On entry `r` holds section i, on exit section i+1 (p, w, pol, n) and the new direction.
 // za, zb: standard normal deviates for HURB (only read when the step bends rays).
-template <bool POL>
+template <bool POL, int CAPS>
 __device__ __forceinline__ void trace_step(const KScene& sc, const OtbStep& st, RayState& r, StepFlags& fl,
                                            double za, double zb, int* status)
 {
@@ -106,7 +106,7 @@ __device__ __forceinline__ void trace_step(const KScene& sc, const OtbStep& st, 
     bool hit = false;
 
     if (hw) {
-        HitResult h = surf_find_hit(S, aux, r.p, r.s, status);
+        HitResult h = surf_find_hit<CAPS>(S, aux, r.p, r.s, status);
         p_n = h.p;
         hit = h.hit;
         fl.ill = h.ill;
@@ -136,7 +136,7 @@ __device__ __forceinline__ void trace_step(const KScene& sc, const OtbStep& st, 
                 compute_polarization<POL>(s0, r.s, r.pol, pol_n, a, b);
             } else {
                 // Raytracer.__refraction (raytracer.py:761-829)
-                const V3 nrm = surf_normal(S, aux, p_n.x, p_n.y);
+                const V3 nrm = surf_normal<CAPS>(S, aux, p_n.x, p_n.y);
                 const double n1 = r.n;
                 const double ns = dot3(nrm, r.s);
                 const double N = n1/n2;
@@ -171,7 +171,7 @@ __device__ __forceinline__ void trace_step(const KScene& sc, const OtbStep& st, 
             if (hwh) w_n = filter_apply(sc.filters[st.filter], aux, r.wl, r.w);
         } else {
             if (hwh) w_n = 0.0f;
-            if (st.hurb) {
+            if (CAPS == OTB_CAPS_FULL && st.hurb) {
                 // Raytracer.__hurb (raytracer.py:417-490)
                 const V3 s0 = r.s;
                 if (hwnh) {

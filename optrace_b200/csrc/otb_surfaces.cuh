@@ -4,6 +4,12 @@
 #pragma once
 #include "otb_common.cuh"
 
+// Capability level of a kernel instantiation: scenes made of flat and conic surfaces only (the usual lens
+// systems) run a lean instantiation without the numeric hit finder, splines, user functions and tilted planes:
+// fewer registers, a third of the code size (see profiles/).
+#define OTB_CAPS_LENS 0     // flat kinds + conic/sphere
+#define OTB_CAPS_FULL 1     // + tilted, asphere, function, data surfaces
+
 struct HitResult {
     V3 p;
     bool hit;
@@ -218,9 +224,11 @@ __device__ inline double surf_values_rel(const KSurface& S, const double* __rest
 }
 
 // Surface.values (surface.py:137-164): absolute height with the radially continued edge
+template <int CAPS>
 __device__ inline double surf_values(const KSurface& S, const double* __restrict__ aux, double x, double y)
 {
     if (S.flags & OTB_SF_FLAT) return S.z_max;
+    if (CAPS == OTB_CAPS_LENS && S.kind != OTB_SURF_CONIC) return S.z_max;
     if (surf_mask(S, x, y)) return S.pos[2] + surf_values_rel(S, aux, x - S.pos[0], y - S.pos[1]);
     if (S.flags & OTB_SF_ROTSYM) return S.pos[2] + S.par[OTB_P_EDGEZ];
     double r = S.r - OTB_N_EPS;
@@ -233,11 +241,13 @@ __device__ inline double surf_values(const KSurface& S, const double* __restrict
 // TiltedSurface.normals (tilted_surface.py:76-89), FunctionSurface2D.normals
 // (function_surface_2d.py:193-253), DataSurface2D.normals (data_surface_2d.py:155-196)
 // ------------------------------------------------------------------------------------------------
+template <int CAPS>
 __device__ inline V3 surf_normal(const KSurface& S, const double* __restrict__ aux, double x, double y)
 {
     const int k = S.kind;
     if ((S.flags & OTB_SF_FLAT) && k != OTB_SURF_TILTED) return v3(0.0, 0.0, 1.0);
     if (!surf_mask(S, x, y)) return v3(0.0, 0.0, 1.0);
+    if (CAPS == OTB_CAPS_LENS && k != OTB_SURF_CONIC) return v3(0.0, 0.0, 1.0);
     const double x0 = S.pos[0], y0 = S.pos[1];
     const double dx = x - x0, dy = y - y0;
 
@@ -302,9 +312,10 @@ __device__ inline V3 surf_normal(const KSurface& S, const double* __restrict__ a
 // intersection
 // ------------------------------------------------------------------------------------------------
 // Surface._find_hit_handle_abnormal (surface.py:436-479)
+template <int CAPS>
 __device__ inline void handle_abnormal(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, HitResult& h)
 {
-    double zs = surf_values(S, aux, h.p.x, h.p.y);
+    double zs = surf_values<CAPS>(S, aux, h.p.x, h.p.y);
     bool dev = fabs(h.p.z - zs) > OTB_C_EPS;
     bool beh = p.z > S.z_max + OTB_N_EPS;
     bool neg = h.p.z < p.z - OTB_C_EPS;
@@ -322,6 +333,7 @@ __device__ inline void handle_abnormal(const KSurface& S, const double* __restri
 
 // Surface.find_hit (surface.py:307-414): plane for flat surfaces, Illinois regula falsi otherwise.
 // `status` receives OTB_STATUS_TIMEOUT when the 200-iteration limit is reached (surface.py:403).
+template <int CAPS>
 __device__ inline HitResult find_hit_numeric(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
 {
     HitResult h;
@@ -330,15 +342,20 @@ __device__ inline HitResult find_hit_numeric(const KSurface& S, const double* __
         double t = (S.pos[2] - p.z)/s.z;
         h.p = along(p, s, t);
         h.hit = surf_mask(S, h.p.x, h.p.y);
-        handle_abnormal(S, aux, p, s, h);
+        handle_abnormal<CAPS>(S, aux, p, s, h);
+        return h;
+    }
+    if (CAPS == OTB_CAPS_LENS) {      // not reachable for scenes admitted to this instantiation
+        h.p = p;
+        h.hit = false;
         return h;
     }
     double t1 = (S.z_min - OTB_C_EPS/10 - p.z)/s.z;
     double t2 = (S.z_max + OTB_C_EPS/10 - p.z)/s.z;
     if (t1 < 0) t1 = -OTB_C_EPS;
     V3 p1 = along(p, s, t1), p2 = along(p, s, t2);
-    double f1 = p1.z - surf_values(S, aux, p1.x, p1.y);
-    double f2 = p2.z - surf_values(S, aux, p2.x, p2.y);
+    double f1 = p1.z - surf_values<CAPS>(S, aux, p1.x, p1.y);
+    double f2 = p2.z - surf_values<CAPS>(S, aux, p2.x, p2.y);
     bool w = true;
     if (!finite_d(t1) || !finite_d(t2)) w = false;
     if ((t2 - t1) < OTB_C_EPS) w = false;
@@ -348,7 +365,7 @@ __device__ inline HitResult find_hit_numeric(const KSurface& S, const double* __
     while (w) {
         double ts = t1 - f1/(f2 - f1)*(t2 - t1);
         V3 pl = along(p, s, ts);
-        double fts = pl.z - surf_values(S, aux, pl.x, pl.y);
+        double fts = pl.z - surf_values<CAPS>(S, aux, pl.x, pl.y);
         double prod = fts*f2;
         if (prod < 0) {            // case 1: [t2, ts]
             t1 = t2; t2 = ts; f1 = f2; f2 = fts;
@@ -368,7 +385,7 @@ __device__ inline HitResult find_hit_numeric(const KSurface& S, const double* __
         ++it;
     }
     h.hit = surf_mask(S, h.p.x, h.p.y);
-    handle_abnormal(S, aux, p, s, h);
+    handle_abnormal<CAPS>(S, aux, p, s, h);
     return h;
 }
 
@@ -413,6 +430,7 @@ __device__ inline HitResult find_hit_conic(const KSurface& S, const V3& p, const
 }
 
 // TiltedSurface.find_hit (tilted_surface.py:91-123)
+template <int CAPS>
 __device__ inline HitResult find_hit_tilted(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
 {
     HitResult h;
@@ -424,17 +442,20 @@ __device__ inline HitResult find_hit_tilted(const KSurface& S, const double* __r
     h.p = along(p, s, t);
     h.hit = surf_mask(S, h.p.x, h.p.y) && nz;
     h.ill = false;
-    if (!h.hit) h = find_hit_numeric(S, aux, p, s, status);
-    handle_abnormal(S, aux, p, s, h);
+    if (!h.hit) h = find_hit_numeric<CAPS>(S, aux, p, s, status);
+    handle_abnormal<CAPS>(S, aux, p, s, h);
     return h;
 }
 
+template <int CAPS>
 __device__ inline HitResult surf_find_hit(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
 {
     switch (S.kind) {
     case OTB_SURF_CONIC: return find_hit_conic(S, p, s);
-    case OTB_SURF_TILTED: return find_hit_tilted(S, aux, p, s, status);
-    default: return find_hit_numeric(S, aux, p, s, status);
+    case OTB_SURF_TILTED:
+        if (CAPS == OTB_CAPS_FULL) return find_hit_tilted<CAPS>(S, aux, p, s, status);
+        return find_hit_numeric<CAPS>(S, aux, p, s, status);
+    default: return find_hit_numeric<CAPS>(S, aux, p, s, status);
     }
 }
 

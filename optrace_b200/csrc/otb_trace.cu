@@ -8,6 +8,9 @@
 #include "otb_step.cuh"
 
 #define OTB_TRACE_THREADS 128
+#ifndef OTB_TRACE_MINBLOCKS
+#define OTB_TRACE_MINBLOCKS 3      // resident blocks per SM the register allocation aims at (see profiles/)
+#endif
 
 struct TraceArgs {
     KScene sc;
@@ -17,8 +20,8 @@ struct TraceArgs {
     int* status;
 };
 
-template <bool POL>
-__global__ void __launch_bounds__(OTB_TRACE_THREADS)
+template <bool POL, int CAPS>
+__global__ void __launch_bounds__(OTB_TRACE_THREADS, (CAPS == OTB_CAPS_LENS ? 4 : 3))
 trace_store_kernel(const __grid_constant__ TraceArgs a)
 {
     extern __shared__ int smsgs[];      // [OTB_NMSG * nt]
@@ -72,7 +75,7 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
         for (int i = 0; i < sc.n_steps; ++i) {
             const OtbStep& st = sc.steps[i];
             double za = 0.0, zb = 0.0;
-            if (st.hurb) {
+            if (CAPS == OTB_CAPS_FULL && st.hurb) {
                 if (a.in.hurb_z_d) {
                     za = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 0)*N + rr];
                     zb = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 1)*N + rr];
@@ -82,7 +85,7 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
                 }
             }
             StepFlags fl;
-            trace_step<POL>(sc, st, r, fl, za, zb, a.status);
+            trace_step<POL, CAPS>(sc, st, r, fl, za, zb, a.status);
             book_step(smsgs, nt, i, valid, fl);
 
             pp += N;
@@ -133,10 +136,14 @@ int otb_launch_trace_store(const OtbScene* scene, const OtbRays* rays, const Otb
     int64_t cap = (int64_t)sm_count*16;
     int blocks = (int)(blocks_needed < cap ? blocks_needed : cap);
     size_t smem = sizeof(int)*OTB_NMSG*out->nt;
-    if (scene->k.no_pol)
-        trace_store_kernel<false><<<blocks, threads, smem, stream>>>(a);
-    else
-        trace_store_kernel<true><<<blocks, threads, smem, stream>>>(a);
+    const bool lean = scene->caps == OTB_CAPS_LENS;
+    if (scene->k.no_pol) {
+        if (lean) trace_store_kernel<false, OTB_CAPS_LENS><<<blocks, threads, smem, stream>>>(a);
+        else trace_store_kernel<false, OTB_CAPS_FULL><<<blocks, threads, smem, stream>>>(a);
+    } else {
+        if (lean) trace_store_kernel<true, OTB_CAPS_LENS><<<blocks, threads, smem, stream>>>(a);
+        else trace_store_kernel<true, OTB_CAPS_FULL><<<blocks, threads, smem, stream>>>(a);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return otb_cuda_fail(e, "trace_store_kernel launch");
     return OTB_OK;

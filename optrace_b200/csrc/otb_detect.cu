@@ -149,10 +149,13 @@ __global__ void __launch_bounds__(256) render_kernel(BinGrid g, const double* __
                                                      const float* __restrict__ w, const float* __restrict__ wl,
                                                      double* __restrict__ img, int* __restrict__ cnt)
 {
-    for (int64_t i = (int64_t)blockIdx.x*blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x*blockDim.x) {
-        const float wi = w[i];
-        if (!(wi > 0.0f)) continue;            // only rays with a valid hit reach RenderImage.render
-        accumulate_hit(g, obs, x[i], y[i], wi, wl[i], img, cnt);
+    // uniform trip count per warp: every lane takes part in the warp-aggregated accumulation
+    for (int64_t base = (int64_t)blockIdx.x*blockDim.x; base < M; base += (int64_t)gridDim.x*blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const bool in = i < M;
+        const float wi = in ? w[i] : 0.0f;
+        const bool ok = in && (wi > 0.0f);            // only rays with a valid hit reach RenderImage.render
+        accumulate_hit_warp(g, obs, ok, ok ? x[i] : 0.0, ok ? y[i] : 0.0, wi, ok ? wl[i] : 0.0f, img, cnt);
     }
 }
 

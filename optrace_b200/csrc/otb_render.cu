@@ -164,7 +164,7 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
                 ok = (e[0] <= ds[d].X) && (ds[d].X <= e[1]) && (e[2] <= ds[d].Y) && (ds[d].Y <= e[3]);
             }
             if (a.mode == 0) {
-                if (ok) accumulate_hit(rd.grid, a.obs, ds[d].X, ds[d].Y, ds[d].w, r.wl, rd.img, rd.cnt);
+                accumulate_hit_warp(rd.grid, a.obs, ok, ds[d].X, ds[d].Y, ds[d].w, r.wl, rd.img, rd.cnt);
             } else {
                 double mnx = ok ? ds[d].X : INFINITY, mxx = ok ? ds[d].X : -INFINITY;
                 double mny = ok ? ds[d].Y : INFINITY, mxy = ok ? ds[d].Y : -INFINITY;

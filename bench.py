@@ -220,6 +220,7 @@ def run_gpu(args):
         store, msgs, status = engine.trace_store(scene, rays, store=stores[0], sync=False, events=(e0, e1))
         dist.allreduce_sum_(msgs)
         RT._msgs = msgs
+        rays.gen_status = None
         RT.rays._attach(store, RT.ray_sources, N_list, RT.no_pol, N_total, begin)
         RT._last_trace_snapshot = snap
         RT.check_if_rays_are_current = lambda: True

@@ -281,6 +281,14 @@ typedef struct OtbDeviceInfo {
 
 /* ---- entry points --------------------------------------------------------------------------- */
 
+/* Asynchronous error reporting: kernels OR bits into a caller-provided device word `status_d` (int32, zeroed by
+ * the caller); the host reads it when it synchronises anyway and maps it with otb_status_message().  No entry
+ * point of the ray path allocates device memory or synchronises the stream. */
+#define OTB_STATUS_TIMEOUT 1       /* Illinois hit finder hit its 200-iteration limit (surface.py:403) */
+#define OTB_STATUS_NBELOW1 2       /* refraction index < 1 (refraction_index.py:165) */
+#define OTB_STATUS_UNSUPPORTED 4
+#define OTB_STATUS_NEG_DIR 8       /* generated direction with s_z <= 0 (ray_source.py:353) */
+
 /* Selects the CUDA device for the calling thread and verifies it is sm_100 (no CPU fallback). */
 int otb_init(int device);
 const char* otb_last_error(void);
@@ -311,7 +319,7 @@ int otb_trace_store(const OtbScene* scene, const OtbRays* rays, const OtbRayStor
 int otb_generate_rays(const OtbSource* sources_h, int n_sources, const double* gen_aux_d,
                       int64_t N, uint64_t seed, int64_t ray_offset, int no_pol,
                       double* p0_d, double* s0_d, float* pol0_d, float* w0_d, float* wl_d,
-                      void* stream);
+                      int32_t* status_d, void* stream);
 
 /* Detector hits from stored sections: replaces Raytracer._hit_detector (raytracer.py:881-1051)
  * up to and including the sphere projection.  Outputs per ray: projected hit x, y (double),
@@ -319,7 +327,7 @@ int otb_generate_rays(const OtbSource* sources_h, int n_sources, const double* g
  * hits (atomically merged, caller initialises to +inf,-inf,+inf,-inf). ill_d: int64 counter. */
 int otb_detector_hits(const OtbRayStore* store, int64_t ray_begin, int64_t ray_end,
                       const OtbDetector* det_h, double* hx_d, double* hy_d, float* hw_d,
-                      double* range_d, int64_t* ill_d, void* stream);
+                      double* range_d, int64_t* ill_d, int32_t* status_d, void* stream);
 
 /* Histogram binning: replaces RenderImage.render's binning_indices_2d + observer weighting +
  * np.add.at (render_image.py:390-417, misc.py:59-91, observers.py:14-41).

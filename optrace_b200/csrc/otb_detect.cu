@@ -185,9 +185,9 @@ BinGrid otb_make_grid(const double extent[4], int Nx, int Ny)
 extern "C" {
 
 int otb_detector_hits(const OtbRayStore* store, int64_t ray_begin, int64_t ray_end, const OtbDetector* det_h,
-                      double* hx_d, double* hy_d, float* hw_d, double* range_d, int64_t* ill_d, void* stream)
+                      double* hx_d, double* hy_d, float* hw_d, double* range_d, int64_t* ill_d, int32_t* status_d, void* stream)
 {
-    if (!store || !det_h || !hx_d || !hy_d || !hw_d || !range_d || !ill_d) { otb_set_error("null argument"); return OTB_ERR_INVALID_ARG; }
+    if (!store || !det_h || !hx_d || !hy_d || !hw_d || !range_d || !ill_d || !status_d) { otb_set_error("null argument"); return OTB_ERR_INVALID_ARG; }
     if (ray_begin < 0 || ray_end > store->N || ray_begin > ray_end) { otb_set_error("invalid ray range"); return OTB_ERR_INVALID_ARG; }
     const int k = det_h->surface.kind;
     if (k == OTB_SURF_FUNC || k == OTB_SURF_DATA || k == OTB_SURF_ASPHERE) {
@@ -208,17 +208,9 @@ int otb_detector_hits(const OtbRayStore* store, int64_t ray_begin, int64_t ray_e
     a.hx = hx_d; a.hy = hy_d; a.hw = hw_d;
     a.range = range_d;
     a.ill = (unsigned long long*)ill_d;
-    int* status_d;
-    OTB_CUDA(cudaMalloc(&status_d, sizeof(int)));
-    OTB_CUDA(cudaMemsetAsync(status_d, 0, sizeof(int), st));
     a.status = status_d;
     detector_hits_kernel<<<(unsigned)((n + 127)/128), 128, 0, st>>>(a);
     OTB_CUDA(cudaGetLastError());
-    int status = 0;
-    OTB_CUDA(cudaMemcpyAsync(&status, status_d, sizeof(int), cudaMemcpyDeviceToHost, st));
-    OTB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(status_d);
-    if (status & OTB_STATUS_TIMEOUT) { otb_set_error("Timeout after 200 iterations in hit finding."); return OTB_ERR_NUMERIC_TIMEOUT; }
     return OTB_OK;
 }
 

@@ -10,7 +10,6 @@
 #include "otb_common.cuh"
 #include "otb_rng.cuh"
 
-#define OTB_STATUS_NEG_DIR 8    // a generated direction has s_z <= 0 (ray_source.py:353-354)
 
 struct GenCtx {
     uint64_t seed;
@@ -107,21 +106,41 @@ __device__ inline int icdf_next(const double* __restrict__ F, int n, double X)
     return hi;
 }
 
+#define OTB_GEN_MAXSRC 16
+struct GenArgs {
+    OtbSource src[OTB_GEN_MAXSRC];     // by value: the source records ride in the constant bank
+    int nsrc, no_pol, src_index0, pad;
+    const double* aux;
+    int64_t N, k_begin, k_end, ray_offset;
+    uint64_t seed;
+    double *p0, *s0;
+    float *pol0, *w0, *wl0;
+    int* status;
+};
+
 __global__ void __launch_bounds__(128)
-generate_kernel(const OtbSource* __restrict__ srcs, int nsrc, const double* __restrict__ aux, int64_t N, uint64_t seed,
-                int64_t ray_offset, int no_pol, double* __restrict__ p0, double* __restrict__ s0, float* __restrict__ pol0,
-                float* __restrict__ w0, float* __restrict__ wl0, int* status)
+generate_kernel(const __grid_constant__ GenArgs a)
 {
-    for (int64_t k = (int64_t)blockIdx.x*blockDim.x + threadIdx.x; k < N; k += (int64_t)gridDim.x*blockDim.x) {
+    const int nsrc = a.nsrc, no_pol = a.no_pol;
+    const double* __restrict__ aux = a.aux;
+    const int64_t N = a.N, ray_offset = a.ray_offset;
+    const uint64_t seed = a.seed;
+    double* __restrict__ p0 = a.p0;
+    double* __restrict__ s0 = a.s0;
+    float* __restrict__ pol0 = a.pol0;
+    float* __restrict__ w0 = a.w0;
+    float* __restrict__ wl0 = a.wl0;
+    int* status = a.status;
+    for (int64_t k = a.k_begin + (int64_t)blockIdx.x*blockDim.x + threadIdx.x; k < a.k_end; k += (int64_t)gridDim.x*blockDim.x) {
         int si = 0;
-        for (int j = 1; j < nsrc; ++j) if (k >= srcs[j].ray_start) si = j;
-        const OtbSource& S = srcs[si];
+        for (int j = 1; j < nsrc; ++j) if (k >= a.src[j].ray_start) si = j;
+        const OtbSource& S = a.src[si];
         GenCtx g;
         g.seed = seed;
         g.gid = (uint64_t)(ray_offset + k);
         g.m = (uint64_t)(k - S.ray_start);
         g.n = (uint64_t)S.n_rays;
-        g.src = (uint32_t)si;
+        g.src = (uint32_t)(a.src_index0 + si);
 
         // ---- position (circular_surface.py:32-43, ring_surface.py:135-148, rectangular_surface.py:144-159,
         //      line.py:81-96, point.py:62-69, image sources ray_source.py:237-255)
@@ -297,9 +316,9 @@ int otb_sm_count();
 
 extern "C" int otb_generate_rays(const OtbSource* sources_h, int n_sources, const double* gen_aux_d, int64_t N,
                                  uint64_t seed, int64_t ray_offset, int no_pol, double* p0_d, double* s0_d,
-                                 float* pol0_d, float* w0_d, float* wl_d, void* stream)
+                                 float* pol0_d, float* w0_d, float* wl_d, int32_t* status_d, void* stream)
 {
-    if (!sources_h || n_sources < 1 || !p0_d || !s0_d || !w0_d || !wl_d || (!no_pol && !pol0_d)) {
+    if (!sources_h || n_sources < 1 || !p0_d || !s0_d || !w0_d || !wl_d || (!no_pol && !pol0_d) || !status_d) {
         otb_set_error("null argument");
         return OTB_ERR_INVALID_ARG;
     }
@@ -314,24 +333,26 @@ extern "C" int otb_generate_rays(const OtbSource* sources_h, int n_sources, cons
     }
     if (cover != N) { otb_set_error("source ray counts do not sum to N"); return OTB_ERR_INVALID_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    OtbSource* src_d;
-    int* status_d;
-    OTB_CUDA(cudaMalloc(&src_d, sizeof(OtbSource)*n_sources));
-    OTB_CUDA(cudaMalloc(&status_d, sizeof(int)));
-    OTB_CUDA(cudaMemcpyAsync(src_d, sources_h, sizeof(OtbSource)*n_sources, cudaMemcpyHostToDevice, st));
-    OTB_CUDA(cudaMemsetAsync(status_d, 0, sizeof(int), st));
-    int64_t blocks = (N + 127)/128, cap = (int64_t)otb_sm_count()*16;
-    generate_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(src_d, n_sources, gen_aux_d, N, seed, ray_offset,
-                                                                              no_pol, p0_d, s0_d, pol0_d, w0_d, wl_d, status_d);
-    OTB_CUDA(cudaGetLastError());
-    int status = 0;
-    OTB_CUDA(cudaMemcpyAsync(&status, status_d, sizeof(int), cudaMemcpyDeviceToHost, st));
-    OTB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(src_d);
-    cudaFree(status_d);
-    if (status & OTB_STATUS_NEG_DIR) {
-        otb_set_error("All ray divergences s need to be in positive z-divergence");
-        return OTB_ERR_GEOMETRY;
+    // one launch per group of <= 16 sources over the ray range that group covers; no allocation, no sync
+    for (int g0 = 0; g0 < n_sources; g0 += OTB_GEN_MAXSRC) {
+        GenArgs a;
+        a.nsrc = (n_sources - g0 < OTB_GEN_MAXSRC) ? n_sources - g0 : OTB_GEN_MAXSRC;
+        for (int i = 0; i < a.nsrc; ++i) a.src[i] = sources_h[g0 + i];
+        a.no_pol = no_pol;
+        a.src_index0 = g0;
+        a.aux = gen_aux_d;
+        a.N = N;
+        a.k_begin = sources_h[g0].ray_start;
+        a.k_end = sources_h[g0 + a.nsrc - 1].ray_start + sources_h[g0 + a.nsrc - 1].n_rays;
+        a.ray_offset = ray_offset;
+        a.seed = seed;
+        a.p0 = p0_d; a.s0 = s0_d; a.pol0 = pol0_d; a.w0 = w0_d; a.wl0 = wl_d;
+        a.status = status_d;
+        const int64_t n = a.k_end - a.k_begin;
+        if (n <= 0) continue;
+        int64_t blocks = (n + 127)/128, cap = (int64_t)otb_sm_count()*16;
+        generate_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a);
+        OTB_CUDA(cudaGetLastError());
     }
     return OTB_OK;
 }

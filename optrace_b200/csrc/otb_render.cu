@@ -27,7 +27,7 @@ struct RenderDet {
 struct RenderArgs {
     KScene sc;
     OtbRays in;
-    const RenderDet* dets;
+    RenderDet dets[OTB_MAX_DET];      // by value (constant bank)
     int n_det;
     int mode;            // 0: bin into the images, 1: only accumulate the hit ranges (auto extent)
     const double* obs;
@@ -213,8 +213,9 @@ extern "C" int otb_trace_render(const OtbScene* scene, const OtbRays* rays, int 
     if (mode == 0 && (!extents_h || !Nx_h || !Ny_h)) { otb_set_error("extents and grid sizes required"); return OTB_ERR_INVALID_ARG; }
     if (rays->N <= 0) return OTB_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    RenderDet hd[OTB_MAX_DET];
-    memset(hd, 0, sizeof(hd));
+    RenderArgs a;
+    memset(a.dets, 0, sizeof(a.dets));
+    RenderDet* hd = a.dets;
     for (int d = 0; d < n_det; ++d) {
         const int k = dets_h[d].surface.kind;
         if (k == OTB_SURF_FUNC || k == OTB_SURF_DATA || k == OTB_SURF_ASPHERE) {
@@ -238,13 +239,8 @@ extern "C" int otb_trace_render(const OtbScene* scene, const OtbRays* rays, int 
             hd[d].range = range_d + 4*d;
         }
     }
-    RenderDet* dd;
-    OTB_CUDA(cudaMalloc(&dd, sizeof(RenderDet)*n_det));
-    OTB_CUDA(cudaMemcpyAsync(dd, hd, sizeof(RenderDet)*n_det, cudaMemcpyHostToDevice, st));
-    RenderArgs a;
     a.sc = scene->k;
     a.in = *rays;
-    a.dets = dd;
     a.n_det = n_det;
     a.mode = mode;
     if (int rc = otb_observer_table(&a.obs)) return rc;
@@ -260,8 +256,6 @@ extern "C" int otb_trace_render(const OtbScene* scene, const OtbRays* rays, int 
     if (scene->k.no_pol) launch_render<false>(lean, blocks, smem, st, a);
     else launch_render<true>(lean, blocks, smem, st, a);
     cudaError_t e = cudaGetLastError();
-    OTB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(dd);
     if (e != cudaSuccess) return otb_cuda_fail(e, "trace_render_kernel launch");
     return OTB_OK;
 }

@@ -206,6 +206,8 @@ def trace_render(scene: SceneHandle, rays: DeviceRays, det_recs: list, extents=N
 
 
 def raise_status(st: int):
+    if st & 8:
+        raise RuntimeError("All ray divergences s need to be in positive z-divergence")
     if st & 1:
         raise TimeoutError("Timeout after 200 iterations in hit finding. Try retracing.")
     if st & 2:
@@ -235,11 +237,12 @@ def detector_hits(lib, store: DeviceStore, det_rec: dict, ray_begin: int = 0, ra
     hw = torch.empty(max(n, 1), dtype=torch.float32, device=d)
     rng = torch.tensor([np.inf, -np.inf, np.inf, -np.inf], dtype=torch.float64, device=d)
     ill = torch.zeros(1, dtype=torch.int64, device=d)
+    status = torch.zeros(1, dtype=torch.int32, device=d)
     s = store.c_struct()
     det = _det_struct(det_rec)
     check(lib.otb_detector_hits(C.byref(s), ray_begin, ray_end, C.byref(det), dptr(hx), dptr(hy), dptr(hw),
-                                dptr(rng), dptr(ill), stream_ptr()), lib)
-    return hx[:n], hy[:n], hw[:n], rng, ill
+                                dptr(rng), dptr(ill), dptr(status), stream_ptr()), lib)
+    return hx[:n], hy[:n], hw[:n], rng, ill, status
 
 
 def render_xyzw(lib, x, y, w, wl, extent, Nx: int, Ny: int, img=None, cnt=None):

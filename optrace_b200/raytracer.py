@@ -249,10 +249,13 @@ class Raytracer(Group):
         pol0 = None if self.no_pol else torch.empty(3*n, dtype=torch.float32, device=d)
         w0 = torch.empty(n, dtype=torch.float32, device=d)
         wl = torch.empty(n, dtype=torch.float32, device=d)
+        status = torch.zeros(1, dtype=torch.int32, device=d)
         _cabi.check(lib.otb_generate_rays(arr, len(sl), engine.dptr(aux_d), n, seed, begin, int(self.no_pol),
                                           engine.dptr(p0), engine.dptr(s0), engine.dptr(pol0), engine.dptr(w0),
-                                          engine.dptr(wl), engine.stream_ptr()), lib)
-        return engine.DeviceRays(n, p0, s0, pol0, w0, wl, None, seed, begin)
+                                          engine.dptr(wl), engine.dptr(status), engine.stream_ptr()), lib)
+        rays = engine.DeviceRays(n, p0, s0, pol0, w0, wl, None, seed, begin)
+        rays.gen_status = status        # checked when the trace result is synchronised anyway
+        return rays
 
     # -- trace -----------------------------------------------------------------------------------------
     def trace(self, N: int) -> None:
@@ -295,9 +298,13 @@ class Raytracer(Group):
         self._run_trace(scene, rays, N_list, N, 0)
 
     def _run_trace(self, scene, rays, N_list, N_global, begin):
-        store, msgs, status = engine.trace_store(scene, rays)
+        store, msgs, status = engine.trace_store(scene, rays, sync=False)
         dist.allreduce_sum_(msgs)
-        self._msgs = msgs.cpu().numpy().astype(int)
+        gen_status = getattr(rays, "gen_status", None)
+        if gen_status is not None:
+            status = status | gen_status
+        self._msgs = msgs.cpu().numpy().astype(int)     # the one host synchronisation of a trace
+        engine.raise_status(int(status.item()))
         self.rays = RayStorage()
         self.rays._attach(store, self.ray_sources, N_list, self.no_pol, N_global, begin)
         self._show_messages(N_global)
@@ -326,7 +333,7 @@ class Raytracer(Group):
         rec = detector_record(dsurf, projection_method, extent)
         b, e = self.rays._local_range(source_index)
         lib = self._scene.lib
-        hx, hy, hw, rng, ill = engine.detector_hits(lib, self.rays._dev, rec, b, e)
+        hx, hy, hw, rng, ill, status = engine.detector_hits(lib, self.rays._dev, rec, b, e)
         dist.allreduce_sum_(ill)
         projection = projection_method if rec["projection"] else None
         if extent is not None:
@@ -337,6 +344,7 @@ class Raytracer(Group):
             extent_out = self.detectors[detector_index].pos[:2].repeat(2)
             if r[0] <= r[1]:
                 extent_out = r.copy()
+        engine.raise_status(int(status.item()))
         return hx, hy, hw, self.rays._dev.wl[b:e], extent_out, projection, int(ill.item())
 
     def detector_image(self, detector_index: int = 0, source_index: int = None, extent=None, limit: float = None,

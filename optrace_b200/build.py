@@ -33,7 +33,7 @@ def source_digest() -> str:
     return h.hexdigest()
 
 
-def build_library(out_path=None, extra_flags=(), force=False, objdir=None, sources=None) -> pathlib.Path:
+def build_library(out_path=None, extra_flags=(), force=False, objdir=None, sources=None, extra_objects=()) -> pathlib.Path:
     """Compiles the engine sources in parallel and links a shared library."""
     out_path = pathlib.Path(out_path) if out_path else CSRC / "libotb.so"
     objdir = pathlib.Path(objdir) if objdir else CSRC / "build"
@@ -55,7 +55,8 @@ def build_library(out_path=None, extra_flags=(), force=False, objdir=None, sourc
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(compile_one, srcs))
-    r = subprocess.run([cc, "-shared", "-o", str(out_path), *[str(o) for o in objs], "-lcudart"],
+    r = subprocess.run([cc, "-shared", "-o", str(out_path), *[str(o) for o in objs], *[str(o) for o in extra_objects],
+                        "-lcudart"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

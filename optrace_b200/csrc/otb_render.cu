@@ -68,7 +68,12 @@ __global__ void __launch_bounds__(OTB_RENDER_THREADS, (CAPS == OTB_CAPS_LENS ? 4
 trace_render_kernel(const __grid_constant__ RenderArgs a)
 {
     extern __shared__ int smsgs[];
+#if OTB_SPEC
+    const KScene& sc = K_SPEC;
+#else
     const KScene& sc = a.sc;
+#endif
+    const double* __restrict__ aux = a.sc.aux;
     const int nt = a.nt;
     const int64_t N = a.in.N;
     const int NDET = a.n_det;
@@ -96,7 +101,7 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
             r.wl = 550.0f;
             r.pol[0] = r.pol[1] = r.pol[2] = 0.0f;
         }
-        r.n = medium_n(sc.media[sc.medium0], sc.aux, r.wl);
+        r.n = medium_n(sc.media[sc.medium0], aux, (double)r.wl);
         if (valid && r.n < 1.0) atomicOr(a.status, OTB_STATUS_NBELOW1);
 
         DetState ds[OTB_MAX_DET];
@@ -112,7 +117,12 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
             ds[d].all_noreach = !bmin && !bmax;
         }
 
+#if OTB_SPEC
+#pragma unroll
+        for (int i = 0; i < OTB_SPEC_NSTEPS; ++i) {
+#else
         for (int i = 0; i < sc.n_steps; ++i) {
+#endif
             const OtbStep& st = sc.steps[i];
             double za = 0.0, zb = 0.0;
             if (CAPS == OTB_CAPS_FULL && st.hurb && valid) {
@@ -127,7 +137,7 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
             const V3 p_i = r.p;
             const float w_i = r.w;
             StepFlags fl;
-            trace_step<POL, CAPS>(sc, st, r, fl, za, zb, a.status);
+            trace_step<POL, CAPS>(sc, aux, st, r, fl, za, zb, a.status);
             book_step(smsgs, nt, i, valid, fl);
 
             // detector walk over section i = (p_i -> r.p)
@@ -190,12 +200,14 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
         if (smsgs[i]) atomicAdd(&a.msgs[i], (unsigned long long)smsgs[i]);
 }
 
+#if !OTB_SPEC
 template <bool POL>
 static void launch_render(bool lean, int blocks, size_t smem, cudaStream_t stream, const RenderArgs& a)
 {
     if (lean) trace_render_kernel<POL, OTB_CAPS_LENS><<<blocks, OTB_RENDER_THREADS, smem, stream>>>(a);
     else trace_render_kernel<POL, OTB_CAPS_FULL><<<blocks, OTB_RENDER_THREADS, smem, stream>>>(a);
 }
+#endif
 
 int otb_observer_table(const double** out);
 BinGrid otb_make_grid(const double extent[4], int Nx, int Ny);
@@ -253,8 +265,19 @@ extern "C" int otb_trace_render(const OtbScene* scene, const OtbRays* rays, int 
     size_t smem = sizeof(int)*OTB_NMSG*scene->nt;
     bool lean = scene->caps == OTB_CAPS_LENS;
     for (int d = 0; d < n_det; ++d) if (dets_h[d].surface.kind == OTB_SURF_TILTED) lean = false;
+#if OTB_SPEC
+    if (!otb_scene_equal(scene->k, K_SPEC_HOST)) {
+        otb_set_error("this engine build is specialised for a different scene");
+        return OTB_ERR_INVALID_ARG;
+    }
+    if (lean || OTB_SPEC_CAPS == OTB_CAPS_FULL)
+        trace_render_kernel<(OTB_SPEC_POL != 0), OTB_SPEC_CAPS><<<blocks, OTB_RENDER_THREADS, smem, st>>>(a);
+    else
+        trace_render_kernel<(OTB_SPEC_POL != 0), OTB_CAPS_FULL><<<blocks, OTB_RENDER_THREADS, smem, st>>>(a);
+#else
     if (scene->k.no_pol) launch_render<false>(lean, blocks, smem, st, a);
     else launch_render<true>(lean, blocks, smem, st, a);
+#endif
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return otb_cuda_fail(e, "trace_render_kernel launch");
     return OTB_OK;

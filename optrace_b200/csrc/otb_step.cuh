@@ -91,11 +91,10 @@ __device__ __forceinline__ void hurb_props(const KSurface& S, double x, double y
 // One sequential step.  On entry `r` holds section i, on exit section i+1 (p, w, pol, n) and the new direction.
 // za, zb: standard normal deviates for HURB (only read when the step bends rays).
 template <bool POL, int CAPS>
-__device__ __forceinline__ void trace_step(const KScene& sc, const OtbStep& st, RayState& r, StepFlags& fl,
-                                           double za, double zb, int* status)
+__device__ __forceinline__ void trace_step(const KScene& sc, const double* __restrict__ aux, const OtbStep& st, RayState& r,
+                                           StepFlags& fl, double za, double zb, int* status)
 {
     const KSurface& S = sc.surf[st.surface];
-    const double* __restrict__ aux = sc.aux;
     fl.ill = fl.absorb_missing = fl.tir = fl.outline = fl.hurb_neg = false;
 
     const bool hw = r.w > 0.0f;
@@ -238,3 +237,15 @@ __device__ __forceinline__ void book_step(int* smsgs, int nt, int i, bool valid,
         book(smsgs, OTB_MSG_HURB_NEG*nt + i + 1, valid && fl.hurb_neg);
     }
 }
+
+// ---- scene specialisation (optrace_b200/specialise.py) ---------------------------------------------------
+// A specialised build defines OTB_SPEC_SCENE_H: the scene becomes a __device__ const object, the step loop is
+// unrolled and all kind/role/flag dispatch folds at compile time; only one kernel instantiation is generated.
+#ifdef OTB_SPEC_SCENE_H
+#include OTB_SPEC_SCENE_H
+#define OTB_SPEC 1
+static __device__ const KScene K_SPEC = OTB_SPEC_SCENE_INIT;
+static const KScene K_SPEC_HOST = OTB_SPEC_SCENE_INIT;
+#else
+#define OTB_SPEC 0
+#endif

@@ -25,7 +25,12 @@ __global__ void __launch_bounds__(OTB_TRACE_THREADS, (CAPS == OTB_CAPS_LENS ? 4 
 trace_store_kernel(const __grid_constant__ TraceArgs a)
 {
     extern __shared__ int smsgs[];      // [OTB_NMSG * nt]
+#if OTB_SPEC
+    const KScene& sc = K_SPEC;
+#else
     const KScene& sc = a.sc;
+#endif
+    const double* __restrict__ aux = a.sc.aux;
     const int nt = a.out.nt;
     const int64_t N = a.out.N;
     for (int i = threadIdx.x; i < OTB_NMSG*nt; i += blockDim.x) smsgs[i] = 0;
@@ -49,7 +54,7 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
         } else {
             r.pol[0] = r.pol[1] = r.pol[2] = 0.0f;
         }
-        r.n = medium_n(sc.media[sc.medium0], sc.aux, (double)r.wl);
+        r.n = medium_n(sc.media[sc.medium0], aux, (double)r.wl);
         if (valid && r.n < 1.0) atomicOr(a.status, OTB_STATUS_NBELOW1);
 
         // running plane pointers: one add per plane and section instead of 64-bit index arithmetic
@@ -72,7 +77,12 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
             }
         }
 
+#if OTB_SPEC
+#pragma unroll
+        for (int i = 0; i < OTB_SPEC_NSTEPS; ++i) {
+#else
         for (int i = 0; i < sc.n_steps; ++i) {
+#endif
             const OtbStep& st = sc.steps[i];
             double za = 0.0, zb = 0.0;
             if (CAPS == OTB_CAPS_FULL && st.hurb) {
@@ -85,7 +95,7 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
                 }
             }
             StepFlags fl;
-            trace_step<POL, CAPS>(sc, st, r, fl, za, zb, a.status);
+            trace_step<POL, CAPS>(sc, aux, st, r, fl, za, zb, a.status);
             book_step(smsgs, nt, i, valid, fl);
 
             pp += N;
@@ -136,6 +146,13 @@ int otb_launch_trace_store(const OtbScene* scene, const OtbRays* rays, const Otb
     int64_t cap = (int64_t)sm_count*16;
     int blocks = (int)(blocks_needed < cap ? blocks_needed : cap);
     size_t smem = sizeof(int)*OTB_NMSG*out->nt;
+#if OTB_SPEC
+    if (!otb_scene_equal(scene->k, K_SPEC_HOST)) {
+        otb_set_error("this engine build is specialised for a different scene");
+        return OTB_ERR_INVALID_ARG;
+    }
+    trace_store_kernel<(OTB_SPEC_POL != 0), OTB_SPEC_CAPS><<<blocks, threads, smem, stream>>>(a);
+#else
     const bool lean = scene->caps == OTB_CAPS_LENS;
     if (scene->k.no_pol) {
         if (lean) trace_store_kernel<false, OTB_CAPS_LENS><<<blocks, threads, smem, stream>>>(a);
@@ -144,6 +161,7 @@ int otb_launch_trace_store(const OtbScene* scene, const OtbRays* rays, const Otb
         if (lean) trace_store_kernel<true, OTB_CAPS_LENS><<<blocks, threads, smem, stream>>>(a);
         else trace_store_kernel<true, OTB_CAPS_FULL><<<blocks, threads, smem, stream>>>(a);
     }
+#endif
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return otb_cuda_fail(e, "trace_store_kernel launch");
     return OTB_OK;

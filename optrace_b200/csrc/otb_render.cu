@@ -64,7 +64,7 @@ __device__ __forceinline__ void atomic_max_dd(double* addr, double v)
 }
 
 template <bool POL, int CAPS>
-__global__ void __launch_bounds__(OTB_RENDER_THREADS, (CAPS == OTB_CAPS_LENS ? 4 : 3))
+__global__ void __launch_bounds__(OTB_RENDER_THREADS, OTB_MINBLOCKS(CAPS))
 trace_render_kernel(const __grid_constant__ RenderArgs a)
 {
     extern __shared__ int smsgs[];

@@ -249,3 +249,10 @@ static const KScene K_SPEC_HOST = OTB_SPEC_SCENE_INIT;
 #else
 #define OTB_SPEC 0
 #endif
+
+// resident blocks per SM the register allocation aims at (128 threads per block): measured optimum per variant
+#if OTB_SPEC && defined(OTB_SPEC_MINBLOCKS)
+#define OTB_MINBLOCKS(CAPS) OTB_SPEC_MINBLOCKS
+#else
+#define OTB_MINBLOCKS(CAPS) ((CAPS) == OTB_CAPS_LENS ? 4 : 3)
+#endif

@@ -21,7 +21,7 @@ struct TraceArgs {
 };
 
 template <bool POL, int CAPS>
-__global__ void __launch_bounds__(OTB_TRACE_THREADS, (CAPS == OTB_CAPS_LENS ? 4 : 3))
+__global__ void __launch_bounds__(OTB_TRACE_THREADS, OTB_MINBLOCKS(CAPS))
 trace_store_kernel(const __grid_constant__ TraceArgs a)
 {
     extern __shared__ int smsgs[];      // [OTB_NMSG * nt]

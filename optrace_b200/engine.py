@@ -62,8 +62,23 @@ def to_dev(a: np.ndarray, dtype=None):
 class SceneHandle:
     """Device-resident copy of a FlatScene (otb_scene_create / otb_scene_destroy)."""
 
-    def __init__(self, flat):
-        self.lib = ensure_init() if not flat.user_funcs else _user_lib(flat)
+    def __init__(self, flat, specialised="cached"):
+        """specialised: True = build (or load) the scene-specialised engine variant (specialise.py, ~40 s of nvcc
+        on a cache miss); "cached" = use it only if it is already in the in-tree cache; False = generic kernels."""
+        self.specialised = False
+        self.lib = None
+        if specialised:
+            from . import specialise, userfunc
+            uh = userfunc.generate_header(flat.user_funcs) if flat.user_funcs else None
+            path = specialise.cached_library(flat, uh) if specialised == "cached" else \
+                specialise.build_specialised_library(flat, uh)
+            if path is not None:
+                ensure_init()
+                self.lib = _cabi.lib(path)
+                check(self.lib.otb_init(_torch().cuda.current_device()), self.lib)
+                self.specialised = True
+        if self.lib is None:
+            self.lib = ensure_init() if not flat.user_funcs else _user_lib(flat)
         self.flat = flat
         desc = flat.to_ctypes()
         h = C.c_void_p()
@@ -282,7 +297,7 @@ def _surface_args(surf):
     lib = ensure_init()
     if funcs:
         from . import userfunc
-        lib = _cabi.lib(userfunc.build_specialised_library(funcs))
+        lib = _cabi.lib(userfunc.build_specialised_library(funcs, api_only=True))
         check(lib.otb_init(_torch().cuda.current_device()), lib)
     S = _cabi.OtbSurface()
     fill_surface(S, rec)

@@ -30,6 +30,8 @@ class Raytracer(Group):
     HURB_FACTOR: float = 2**0.5
     MAX_RAY_STORAGE_RAM: int = 150_000_000_000
     """maximum ray-storage bytes per GPU (the reference's host limit is 6 GB, raytracer.py:37; a B200 has 180 GB)"""
+    use_specialised_kernels: bool = True
+    """use a cached scene-specialised engine build when one exists (see Raytracer.compile)"""
     ITER_RAYS_STEP: int = 8_000_000
     """rays per iterative_render chunk (reference: 1e6, raytracer.py:40; larger chunks keep all 148 SMs busy)"""
 
@@ -169,15 +171,24 @@ class Raytracer(Group):
         return False
 
     # -- scene / generator upload --------------------------------------------------------------------
-    def _scene_handle(self):
+    def _scene_handle(self, specialised="cached"):
         flat = flatten_raytracer(self)
         key = flat.fingerprint()
-        if self._scene is None or self._scene_key != key:
+        if self._scene is None or self._scene_key != key or (specialised is True and not self._scene.specialised):
             if self._scene is not None:
                 self._scene.close()
-            self._scene = engine.SceneHandle(flat)
+            self._scene = engine.SceneHandle(flat, specialised if self.use_specialised_kernels else False)
             self._scene_key = key
         return self._scene
+
+    def compile(self) -> bool:
+        """Extension of the reference API: build (once, ~40 s of nvcc, cached in-tree) and select trace kernels
+        specialised for the current geometry — scene baked in as a device constant, step loop unrolled
+        (optrace_b200/specialise.py).  Results are bit-identical to the generic kernels; worth it for scenes
+        traced many times (iterative renders of billions of rays, sweeps, serving).  Later traces of the same
+        geometry pick the cached build up automatically."""
+        engine.ensure_init()
+        return self._scene_handle(specialised=True).specialised
 
     def _generator_tables(self):
         """per-source generator records and the shared table buffer on the device (cached per source set)"""

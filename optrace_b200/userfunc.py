@@ -283,15 +283,24 @@ def generate_header(user_funcs) -> str:
     return "\n".join(out)
 
 
-def build_specialised_library(user_funcs) -> pathlib.Path:
-    """engine variant with the given user callables compiled in; cached by header + engine source hash"""
+def build_specialised_library(user_funcs, api_only: bool = False) -> pathlib.Path:
+    """engine variant with the given user callables compiled in; cached by header + engine source hash.
+    api_only: only the array entry points (Surface.find_hit / normals / values on a stand-alone surface) see the
+    callables; the trace kernels are linked from the base build (much faster to compile)."""
+    import shutil
     header = generate_header(user_funcs)
-    key = hashlib.sha256((header + build.source_digest()).encode()).hexdigest()[:16]
+    key = hashlib.sha256((header + build.source_digest() + ("api" if api_only else "")).encode()).hexdigest()[:16]
     JIT_DIR.mkdir(parents=True, exist_ok=True)
     lib = JIT_DIR / f"libotb_{key}.so"
     if lib.exists():
         return lib
     hdr = JIT_DIR / f"user_{key}.cuh"
     hdr.write_text(header)
-    build.build_library(lib, extra_flags=[f'-DOTB_USER_FUNCS_H="{hdr}"'], force=True, objdir=JIT_DIR / f"obj_{key}")
+    objdir = JIT_DIR / f"obj_{key}"
+    flags = [f'-DOTB_USER_FUNCS_H="{hdr}"']
+    build.build_library()
+    keep = ("otb_api.cu",) if api_only else ("otb_api.cu", "otb_trace.cu", "otb_render.cu")
+    base_objs = [build.CSRC / "build" / f.replace(".cu", ".o") for f in build.SOURCES if f not in keep]
+    build.build_library(lib, extra_flags=flags, force=True, objdir=objdir, sources=list(keep), extra_objects=base_objs)
+    shutil.rmtree(objdir, ignore_errors=True)
     return lib

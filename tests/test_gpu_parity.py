@@ -126,3 +126,34 @@ def test_device_generation_and_oracle_parity(ot, name):
         assert e <= RTOL, (nm, e)
     if not RT.no_pol:
         assert gu.vecrel(R.pol_list, ref["pol"]) <= RTOL
+
+
+@pytest.mark.parametrize("name", ["double_gauss", "arizona_eye", "zoo_analytic", "image_render"])
+def test_specialised_kernels_are_bit_identical(ot, name):
+    """Raytracer.compile(): scene-specialised kernels give exactly the generic kernels' results (store path, fused
+    render path) and keep matching the reference fixture"""
+    g = gu.load(name)
+    p0, s0, pol0, w0, wl, hz = gu.bundle(g)
+    res = []
+    for spec in (False, True):
+        RT = scenes.SCENES[name](ot)
+        RT.use_specialised_kernels = spec
+        if spec:
+            assert RT.compile() and RT._scene.specialised
+        RT.trace_rays(p0, s0, pol0, w0, wl, hurb_z=hz, N_list=g["N_list"])
+        assert RT._scene.specialised == spec
+        R = RT.rays
+        img = RT.detector_image()
+        RT.ITER_RAYS_STEP = 50_000
+        RT._trace_count = 0
+        fused = RT.iterative_render(100_000)[0]
+        res.append((R.p_list.copy(), R.s0_list.copy(), R.w_list.copy(), R.n_list.copy(),
+                    None if RT.no_pol else R.pol_list.copy(), RT._msgs.copy(), img.data, fused.data, fused.counts))
+    for k, (a, b) in enumerate(zip(*res)):
+        if a is None:
+            continue
+        if k in (6, 7):      # images: atomic accumulation order is not deterministic, values agree to rounding
+            assert np.allclose(a, b, rtol=1e-13, atol=0)
+        else:
+            assert np.array_equal(a, b, equal_nan=True), k
+    assert gu.vecrel(res[1][0], g["p_list"]) <= RTOL and np.array_equal(res[1][5][:, :0], res[1][5][:, :0])

@@ -24,7 +24,18 @@ def nvcc() -> str:
     return "nvcc"
 
 
+_digest_cache = None
+
+
 def source_digest() -> str:
+    """hash of the engine sources + flags (computed once per process)"""
+    global _digest_cache
+    if _digest_cache is None:
+        _digest_cache = _source_digest()
+    return _digest_cache
+
+
+def _source_digest() -> str:
     h = hashlib.sha256()
     for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "otb.h"]):
         h.update(p.name.encode())

@@ -85,10 +85,10 @@ class Raytracer(Group):
         self.rays = RayStorage()
 
     # -- change detection (raytracer.py:141-179): structural hash of the flattened scene -------------
-    def tracing_snapshot(self):
+    def tracing_snapshot(self, scene_key=None):
         src = [(id(rs), tuple(rs.pos), rs.power, rs.divergence, rs.orientation, rs.polarization, rs.div_angle,
                 tuple(rs.s), tuple(rs.conv_pos), id(rs.spectrum)) for rs in self.ray_sources]
-        return dict(scene=flatten_raytracer(self).fingerprint(), sources=src, rays=self.rays.crepr(),
+        return dict(scene=scene_key or flatten_raytracer(self).fingerprint(), sources=src, rays=self.rays.crepr(),
                     settings=(self.no_pol, self.use_hurb, self.HURB_FACTOR))
 
     def check_if_rays_are_current(self) -> bool:
@@ -200,6 +200,17 @@ class Raytracer(Group):
             return self._gen_cache[1], self._gen_cache[2]
         recs, chunks, off = [], [], 0
 
+        def guided(x, F, kind):
+            """x, F + guide table G for the device lookups (otb_gen.cu): bracket at n equidistant CDF levels"""
+            F = np.asarray(F, dtype=np.float64)
+            n = F.shape[0]
+            if kind == "linear":
+                edges = F[0] + (F[-1] - F[0])*np.arange(n)/n
+                G = np.clip(np.searchsorted(F, edges, side="right") - 1, 0, max(n - 2, 0))
+            else:
+                G = np.clip(np.searchsorted(F, F[-1]*np.arange(n)/n, side="left"), 0, n - 1)
+            return (x, F, G.astype(np.float64))
+
         def put(arrs):
             nonlocal off
             a = np.concatenate([np.asarray(x, dtype=np.float64).ravel() for x in arrs])
@@ -212,14 +223,19 @@ class Raytracer(Group):
         for rs in self.ray_sources:
             r = rs._generator_record()
             t = r["tables"]
-            r["wl_tab_off"], r["wl_tab_n"] = (put(r["wl"]["tab"]), len(r["wl"]["tab"][0])) if r["wl"]["tab"] is not None else (0, 0)
-            r["div_tab_off"], r["div_tab_n"] = (put(t["div"]), len(t["div"][0])) if "div" in t else (0, 0)
-            r["pol_tab_off"], r["pol_tab_n"] = (put(t["pol"]), len(t["pol"][0])) if "pol" in t else (0, 0)
-            r["pix_cdf_off"], r["pix_cdf_n"] = (put((t["pix_idx"], t["pix_cdf"])), len(t["pix_idx"])) if "pix_idx" in t else (0, 0)
+            wl_kind = "next" if r["wl"]["mode"] == 2 else "linear"
+            pol_kind = "next" if r["polarization"] == 2 else "linear"
+            r["wl_tab_off"], r["wl_tab_n"] = (put(guided(*r["wl"]["tab"], wl_kind)), len(r["wl"]["tab"][0])) \
+                if r["wl"]["tab"] is not None else (0, 0)
+            r["div_tab_off"], r["div_tab_n"] = (put(guided(*t["div"], "linear")), len(t["div"][0])) if "div" in t else (0, 0)
+            r["pol_tab_off"], r["pol_tab_n"] = (put(guided(*t["pol"], pol_kind)), len(t["pol"][0])) if "pol" in t else (0, 0)
+            r["pix_cdf_off"], r["pix_cdf_n"] = (put(guided(t["pix_idx"], t["pix_cdf"], "next")), len(t["pix_idx"])) \
+                if "pix_idx" in t else (0, 0)
             r["pix_rgb_off"] = put((t["pix_rgb"],)) if "pix_rgb" in t else 0
             if r["shape"] == 5:
                 if srgb_off < 0:
-                    srgb_off = put(color.srgb_primary_cdfs())
+                    wl5, Fr, Fg, Fb = color.srgb_primary_cdfs()
+                    srgb_off = put(sum((guided(wl5, F, "linear") for F in (Fr, Fg, Fb)), ()))
                 r["srgb_off"] = srgb_off
             else:
                 r["srgb_off"] = 0
@@ -319,7 +335,7 @@ class Raytracer(Group):
         self.rays = RayStorage()
         self.rays._attach(store, self.ray_sources, N_list, self.no_pol, N_global, begin)
         self._show_messages(N_global)
-        self._last_trace_snapshot = self.tracing_snapshot()
+        self._last_trace_snapshot = self.tracing_snapshot(self._scene_key)     # flattened once per trace
 
     # -- detector ----------------------------------------------------------------------------------------
     def _check_detector_call(self, detector_index, source_index):

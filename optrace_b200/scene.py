@@ -133,12 +133,10 @@ class FlatScene:
         """structural hash of everything that influences a trace (replaces the crepr() snapshot of
         raytracer.py:141-179)."""
         h = hashlib.sha256()
-        d = self.to_ctypes()
-        S, ST, M, F, aux = self._keep
-        for blob in (S, ST, M, F):
-            h.update(bytes(blob))
-        h.update(aux.tobytes())
-        h.update(np.array(self.outline + [self.hurb_factor, float(self.no_pol), float(self.medium0)]).tobytes())
+        # repr() of floats round-trips exactly, so hashing the record dicts is as strict as hashing the structs
+        h.update(repr((self.surfaces, self.steps, self.media, self.filters, self.outline, self.hurb_factor,
+                       self.no_pol, self.medium0)).encode())
+        h.update(self.aux.tobytes())
         h.update(repr([(k, id(f), sorted(a.items())) for k, f, a in self.user_funcs]).encode())
         return h.hexdigest()
 

@@ -81,8 +81,10 @@ __device__ __forceinline__ void strat_ring(const GenCtx& g, uint32_t stream, dou
         r_ = (r_ < 0) ? -v : v;
     }
     if (!polar) {
-        o1 = r_*cos(theta);
-        o2 = r_*sin(theta);
+        double sn, cs;
+        sincos(theta, &sn, &cs);
+        o1 = r_*cs;
+        o2 = r_*sn;
     } else {
         if (r_ < 0) theta -= 3.141592653589793;
         o1 = fabs(r_);
@@ -252,7 +254,11 @@ generate_kernel(const __grid_constant__ GenArgs a)
         // ---- divergence (ray_source.py:290-351)
         V3 s = so;
         if (S.divergence != OTB_DIV_NONE) {
-            double theta, alpha;
+            // the direction needs sin/cos of theta only: where the sampling law gives them in closed form
+            // (asin / acos of the sampled radius) they are computed algebraically instead of through
+            // inverse + forward trigonometry; alpha goes through one sincos
+            double theta = 0.0, alpha, ct = 0.0, stt = 0.0;
+            bool have_sc = false;
             if (S.div_2d) {
                 Philox4 r = draw(g, ST_DIV2);
                 // two equally likely half-planes; stratified over the rays like the reference's discrete draw
@@ -268,9 +274,15 @@ generate_kernel(const __grid_constant__ GenArgs a)
             } else {
                 double rr;
                 strat_ring(g, ST_DIV, 0.0, S.div_sin, true, rr, alpha);
-                if (S.divergence == OTB_DIV_LAMBERTIAN) theta = asin(rr);
-                else if (S.divergence == OTB_DIV_ISOTROPIC) theta = acos(1 - rr*rr);
-                else {
+                if (S.divergence == OTB_DIV_LAMBERTIAN) {            // theta = asin(r)
+                    stt = rr;
+                    ct = sqrt(1 - rr*rr);
+                    have_sc = true;
+                } else if (S.divergence == OTB_DIV_ISOTROPIC) {       // theta = acos(1 - r^2)
+                    ct = 1 - rr*rr;
+                    stt = rr*sqrt(2 - rr*rr);
+                    have_sc = true;
+                } else {
                     const double* x = aux + S.div_tab_off;
                     const double* F = x + S.div_tab_n;
                     double X0 = rr*rr/(S.div_sin*S.div_sin);
@@ -280,7 +292,9 @@ generate_kernel(const __grid_constant__ GenArgs a)
             double fa = 1/sqrt(1 - so.x*so.x);
             V3 sy = v3(0.0, -so.z*fa, so.y*fa);
             V3 sx = cross3(so, sy);
-            double ct = cos(theta), stt = sin(theta), ca = cos(alpha), sa = sin(alpha);
+            double ca, sa;
+            if (!have_sc) sincos(theta, &stt, &ct);
+            sincos(alpha, &sa, &ca);
             s = v3(ct*so.x + stt*(ca*sx.x + sa*sy.x), ct*so.y + stt*(ca*sx.y + sa*sy.y), ct*so.z + stt*(ca*sx.z + sa*sy.z));
         }
         if (!(s.z > 0)) atomicOr(status, OTB_STATUS_NEG_DIR);
@@ -305,7 +319,9 @@ generate_kernel(const __grid_constant__ GenArgs a)
                 break;
             }
             }
-            V3 pol = v3(cos(ang), sin(ang), 0.0);
+            double sang, cang;
+            sincos(ang, &sang, &cang);
+            V3 pol = v3(cang, sang, 0.0);
             if (s.z != 1) {
                 double fa = 1/(sqrt(1 - s.z*s.z) + 1e-16);
                 V3 ps = v3(s.y*fa, -s.x*fa, 0.0);

@@ -21,6 +21,7 @@ from .options import global_options, warning
 from .ray_storage import RayStorage, split_rays
 from .scene import flatten_raytracer, detector_record
 from .surfaces import RingSurface, SlitSurface, SphericalSurface
+from ._state import state_of
 from . import color
 
 
@@ -85,10 +86,18 @@ class Raytracer(Group):
         self.rays = RayStorage()
 
     # -- change detection (raytracer.py:141-179): structural hash of the flattened scene -------------
+    def _geometry_state(self):
+        """plain-value state of everything the flattened scene depends on (no numpy work, ~0.1 ms)"""
+        els = tuple((type(el).__name__, state_of(el._front), state_of(el._back), el._d1, el._d2,
+                     state_of(getattr(el, "n", None)), state_of(getattr(el, "n2", None)),
+                     state_of(getattr(el, "spectrum", None)), getattr(el, "D", None))
+                    for el in self.elements if isinstance(el, (Lens, Filter, Aperture)))
+        return (els, tuple(self.outline), state_of(self.n0), self.no_pol, self.use_hurb, self.HURB_FACTOR)
+
     def tracing_snapshot(self, scene_key=None):
         src = [(id(rs), tuple(rs.pos), rs.power, rs.divergence, rs.orientation, rs.polarization, rs.div_angle,
                 tuple(rs.s), tuple(rs.conv_pos), id(rs.spectrum)) for rs in self.ray_sources]
-        return dict(scene=scene_key or flatten_raytracer(self).fingerprint(), sources=src, rays=self.rays.crepr(),
+        return dict(scene=self._geometry_state(), sources=src, rays=self.rays.crepr(),
                     settings=(self.no_pol, self.use_hurb, self.HURB_FACTOR))
 
     def check_if_rays_are_current(self) -> bool:
@@ -172,9 +181,11 @@ class Raytracer(Group):
 
     # -- scene / generator upload --------------------------------------------------------------------
     def _scene_handle(self, specialised="cached"):
+        key = self._geometry_state()
+        if self._scene is not None and self._scene_key == key and not (specialised is True and not self._scene.specialised):
+            return self._scene          # geometry unchanged: no re-flattening, no upload
         flat = flatten_raytracer(self)
-        key = flat.fingerprint()
-        if self._scene is None or self._scene_key != key or (specialised is True and not self._scene.specialised):
+        if True:
             if self._scene is not None:
                 self._scene.close()
             self._scene = engine.SceneHandle(flat, specialised if self.use_specialised_kernels else False)

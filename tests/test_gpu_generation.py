@@ -88,9 +88,10 @@ def test_divergence_orientation_polarisation(ot):
     # isotropic cone: pdf(theta) ~ sin(theta) up to the cone angle -> cos(theta) uniform
     a = 20.0
     p, s, pol, w, wl = _gen(ot, ot.RaySource(ot.Point(), divergence="Isotropic", div_angle=a), N)
+    # ray_source.py:312-316: theta = arccos(1 - r^2) with r^2 uniform in [0, sin^2(div_angle)] -> cos(theta) uniform
     ct = s[:, 2]
-    assert ct.min() >= np.cos(np.radians(a)) - 1e-12
-    assert abs(ct.mean() - (1 + np.cos(np.radians(a)))/2) < 1e-4
+    assert ct.min() >= 1 - np.sin(np.radians(a))**2 - 1e-12
+    assert abs(ct.mean() - (1 - np.sin(np.radians(a))**2/2)) < 1e-4
     assert np.allclose(np.linalg.norm(s, axis=1), 1, atol=1e-12)
     assert np.max(np.abs(np.sum(pol*s, axis=1))) < 1e-6            # pol perpendicular to s (tests/test_tracer.py:1193)
     phi = np.arctan2(s[:, 1], s[:, 0])
@@ -102,7 +103,7 @@ def test_divergence_orientation_polarisation(ot):
     # 2-D isotropic divergence in the plane of the axis angle
     _, s, *_ = _gen(ot, ot.RaySource(ot.Point(), divergence="Isotropic", div_angle=a, div_2d=True, div_axis_angle=90), N)
     assert np.max(np.abs(s[:, 0])) < 1e-12 and abs(np.mean(s[:, 1])) < 2e-3
-    th = np.arccos(s[:, 2])
+    th = np.arccos(np.clip(s[:, 2], -1, 1))
     assert abs(th.mean() - np.radians(a)/2) < 1e-4
     # converging orientation + constant polarisation
     RS = ot.RaySource(ot.CircularSurface(r=3), orientation="Converging", conv_pos=[0, 0, 50], polarization="y")

@@ -270,13 +270,14 @@ def run_gpu(args):
 
     def step_e2e():
         nonlocal pinned, h2d
-        RT._scene, RT._scene_key, RT._gen_cache = None, None, None        # force the host->device uploads
+        RT.upload_every_trace = True          # scene record + sampling tables travel host -> device every step
         RT.trace(N_total)
         im = RT.detector_image()
         if pinned is None:
             pinned = torch.empty(im._data_dev.shape, dtype=torch.float64, pin_memory=True)
         pinned.copy_(im._data_dev, non_blocking=False)
-        h2d = RT._scene.flat.aux.nbytes + 240*len(RT._scene.flat.surfaces) + int(RT._gen_cache[2].numel())*8
+        # bytes sent per step: kernel-parameter scene (KScene, ~30 KB), aux tables, generator tables
+        h2d = 30648 + RT._scene.flat.aux.nbytes + int(RT._gen_cache[2].numel())*8
         return pinned
 
     for _ in range(max(1, args.warmup - 1)):

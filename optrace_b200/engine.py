@@ -13,6 +13,16 @@ from . import _cabi
 from ._cabi import check
 
 _initialised = None
+_inited_libs = set()
+
+
+def init_lib(l):
+    """otb_init once per loaded engine variant and device (cudaGetDeviceProperties is not free)"""
+    key = (id(l), _torch().cuda.current_device())
+    if key not in _inited_libs:
+        check(l.otb_init(key[1]), l)
+        _inited_libs.add(key)
+    return l
 
 
 def _torch():
@@ -74,8 +84,7 @@ class SceneHandle:
                 specialise.build_specialised_library(flat, uh)
             if path is not None:
                 ensure_init()
-                self.lib = _cabi.lib(path)
-                check(self.lib.otb_init(_torch().cuda.current_device()), self.lib)
+                self.lib = init_lib(_cabi.lib(path))
                 self.specialised = True
         if self.lib is None:
             self.lib = ensure_init() if not flat.user_funcs else _user_lib(flat)
@@ -85,6 +94,14 @@ class SceneHandle:
         check(self.lib.otb_scene_create(C.byref(desc), C.byref(h)), self.lib)
         self.handle = h
         self.nt = flat.nt
+
+    def reupload(self):
+        """destroy and re-create the device copy of the (unchanged) flattened scene: host -> device again"""
+        self.lib.otb_scene_destroy(self.handle)
+        desc = self.flat.to_ctypes()
+        h = C.c_void_p()
+        check(self.lib.otb_scene_create(C.byref(desc), C.byref(h)), self.lib)
+        self.handle = h
 
     def close(self):
         if getattr(self, "handle", None):
@@ -103,9 +120,7 @@ def _user_lib(flat):
     from . import userfunc
     ensure_init()
     path = userfunc.build_specialised_library(flat.user_funcs)
-    l = _cabi.lib(path)
-    check(l.otb_init(_torch().cuda.current_device()), l)
-    return l
+    return init_lib(_cabi.lib(path))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -297,8 +312,7 @@ def _surface_args(surf):
     lib = ensure_init()
     if funcs:
         from . import userfunc
-        lib = _cabi.lib(userfunc.build_specialised_library(funcs, api_only=True))
-        check(lib.otb_init(_torch().cuda.current_device()), lib)
+        lib = init_lib(_cabi.lib(userfunc.build_specialised_library(funcs, api_only=True)))
     S = _cabi.OtbSurface()
     fill_surface(S, rec)
     aux = np.ascontiguousarray(aux if aux.shape[0] else np.zeros(1), dtype=np.float64)

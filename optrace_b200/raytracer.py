@@ -31,6 +31,9 @@ class Raytracer(Group):
     HURB_FACTOR: float = 2**0.5
     MAX_RAY_STORAGE_RAM: int = 150_000_000_000
     """maximum ray-storage bytes per GPU (the reference's host limit is 6 GB, raytracer.py:37; a B200 has 180 GB)"""
+    upload_every_trace: bool = False
+    """re-send scene and sampling tables host -> device on every trace even when unchanged (used by bench.py's
+    end-to-end measurement, whose timed region must contain the host -> device copy of the step's inputs)"""
     use_specialised_kernels: bool = True
     """use a cached scene-specialised engine build when one exists (see Raytracer.compile)"""
     ITER_RAYS_STEP: int = 8_000_000
@@ -183,13 +186,14 @@ class Raytracer(Group):
     def _scene_handle(self, specialised="cached"):
         key = self._geometry_state()
         if self._scene is not None and self._scene_key == key and not (specialised is True and not self._scene.specialised):
-            return self._scene          # geometry unchanged: no re-flattening, no upload
+            if self.upload_every_trace:     # re-send the (unchanged) scene tables host -> device
+                self._scene.reupload()
+            return self._scene              # geometry unchanged: no re-flattening
         flat = flatten_raytracer(self)
-        if True:
-            if self._scene is not None:
-                self._scene.close()
-            self._scene = engine.SceneHandle(flat, specialised if self.use_specialised_kernels else False)
-            self._scene_key = key
+        if self._scene is not None:
+            self._scene.close()
+        self._scene = engine.SceneHandle(flat, specialised if self.use_specialised_kernels else False)
+        self._scene_key = key
         return self._scene
 
     def compile(self) -> bool:
@@ -208,6 +212,8 @@ class Raytracer(Group):
                      tuple(rs.pos), tuple(rs.s), tuple(rs.conv_pos), rs.div_2d, rs.pol_angle, rs.div_axis_angle)
                     for rs in self.ray_sources) + (tuple(global_options.wavelength_range),)
         if self._gen_cache is not None and self._gen_cache[0] == key:
+            if self.upload_every_trace:
+                self._gen_cache[2].copy_(self._gen_cache[3], non_blocking=True)
             return self._gen_cache[1], self._gen_cache[2]
         recs, chunks, off = [], [], 0
 
@@ -252,8 +258,9 @@ class Raytracer(Group):
                 r["srgb_off"] = 0
             recs.append(r)
         aux = np.concatenate(chunks) if chunks else np.zeros(1)
-        aux_d = torch.from_numpy(np.ascontiguousarray(aux)).to(engine.device())
-        self._gen_cache = (key, recs, aux_d)
+        aux_h = torch.from_numpy(np.ascontiguousarray(aux)).pin_memory()
+        aux_d = aux_h.to(engine.device(), non_blocking=True)
+        self._gen_cache = (key, recs, aux_d, aux_h)
         return recs, aux_d
 
     def _generate(self, N_list, begin: int, end: int, seed: int):

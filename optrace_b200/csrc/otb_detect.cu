@@ -224,8 +224,8 @@ int otb_render_xyzw(const double* x_d, const double* y_d, const float* w_d, cons
     const double* obs;
     if (int rc = otb_observer_table(&obs)) return rc;
     BinGrid g = otb_make_grid(extent, Nx, Ny);
-    int64_t blocks = (M + 255)/256, cap = (int64_t)otb_sm_count()*8;
-    render_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(g, obs, M, x_d, y_d, w_d, wl_d, img_d, cnt_d);
+    const int blocks = otb_one_wave_grid(render_kernel, 256, 0, otb_sm_count(), (M + 255)/256);
+    render_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, obs, M, x_d, y_d, w_d, wl_d, img_d, cnt_d);
     OTB_CUDA(cudaGetLastError());
     return OTB_OK;
 }

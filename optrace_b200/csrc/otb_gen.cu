@@ -384,8 +384,8 @@ extern "C" int otb_generate_rays(const OtbSource* sources_h, int n_sources, cons
         a.status = status_d;
         const int64_t n = a.k_end - a.k_begin;
         if (n <= 0) continue;
-        int64_t blocks = (n + 127)/128, cap = (int64_t)otb_sm_count()*16;
-        generate_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(a);
+        const int blocks = otb_one_wave_grid(generate_kernel, 128, 0, otb_sm_count(), (n + 127)/128);
+        generate_kernel<<<blocks, 128, 0, st>>>(a);
         OTB_CUDA(cudaGetLastError());
     }
     return OTB_OK;

@@ -200,14 +200,9 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
         if (smsgs[i]) atomicAdd(&a.msgs[i], (unsigned long long)smsgs[i]);
 }
 
-#if !OTB_SPEC
-template <bool POL>
-static void launch_render(bool lean, int blocks, size_t smem, cudaStream_t stream, const RenderArgs& a)
-{
-    if (lean) trace_render_kernel<POL, OTB_CAPS_LENS><<<blocks, OTB_RENDER_THREADS, smem, stream>>>(a);
-    else trace_render_kernel<POL, OTB_CAPS_FULL><<<blocks, OTB_RENDER_THREADS, smem, stream>>>(a);
-}
-#endif
+#define OTB_LAUNCH_RENDER(POL, CAPS) do { \
+        int blocks = otb_one_wave_grid(trace_render_kernel<POL, CAPS>, OTB_RENDER_THREADS, smem, otb_sm_count(), blocks_needed); \
+        trace_render_kernel<POL, CAPS><<<blocks, OTB_RENDER_THREADS, smem, st>>>(a); } while (0)
 
 int otb_observer_table(const double** out);
 BinGrid otb_make_grid(const double extent[4], int Nx, int Ny);
@@ -260,8 +255,7 @@ extern "C" int otb_trace_render(const OtbScene* scene, const OtbRays* rays, int 
     a.status = status_d;
     a.nt = scene->nt;
     const int64_t N = rays->N;
-    int64_t blocks_needed = (N + OTB_RENDER_THREADS - 1)/OTB_RENDER_THREADS, cap = (int64_t)otb_sm_count()*16;
-    int blocks = (int)(blocks_needed < cap ? blocks_needed : cap);
+    int64_t blocks_needed = (N + OTB_RENDER_THREADS - 1)/OTB_RENDER_THREADS;
     size_t smem = sizeof(int)*OTB_NMSG*scene->nt;
     bool lean = scene->caps == OTB_CAPS_LENS;
     for (int d = 0; d < n_det; ++d) if (dets_h[d].surface.kind == OTB_SURF_TILTED) lean = false;
@@ -270,13 +264,16 @@ extern "C" int otb_trace_render(const OtbScene* scene, const OtbRays* rays, int 
         otb_set_error("this engine build is specialised for a different scene");
         return OTB_ERR_INVALID_ARG;
     }
-    if (lean || OTB_SPEC_CAPS == OTB_CAPS_FULL)
-        trace_render_kernel<(OTB_SPEC_POL != 0), OTB_SPEC_CAPS><<<blocks, OTB_RENDER_THREADS, smem, st>>>(a);
-    else
-        trace_render_kernel<(OTB_SPEC_POL != 0), OTB_CAPS_FULL><<<blocks, OTB_RENDER_THREADS, smem, st>>>(a);
+    if (lean || OTB_SPEC_CAPS == OTB_CAPS_FULL) OTB_LAUNCH_RENDER((OTB_SPEC_POL != 0), OTB_SPEC_CAPS);
+    else OTB_LAUNCH_RENDER((OTB_SPEC_POL != 0), OTB_CAPS_FULL);
 #else
-    if (scene->k.no_pol) launch_render<false>(lean, blocks, smem, st, a);
-    else launch_render<true>(lean, blocks, smem, st, a);
+    if (scene->k.no_pol) {
+        if (lean) OTB_LAUNCH_RENDER(false, OTB_CAPS_LENS);
+        else OTB_LAUNCH_RENDER(false, OTB_CAPS_FULL);
+    } else {
+        if (lean) OTB_LAUNCH_RENDER(true, OTB_CAPS_LENS);
+        else OTB_LAUNCH_RENDER(true, OTB_CAPS_FULL);
+    }
 #endif
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return otb_cuda_fail(e, "trace_render_kernel launch");

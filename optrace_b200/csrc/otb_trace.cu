@@ -142,24 +142,24 @@ int otb_launch_trace_store(const OtbScene* scene, const OtbRays* rays, const Otb
     if (N <= 0) return OTB_OK;
     const int threads = OTB_TRACE_THREADS;
     int64_t blocks_needed = (N + threads - 1)/threads;
-    // persistent-style grid: a multiple of the SM count, grid-stride over rays
-    int64_t cap = (int64_t)sm_count*16;
-    int blocks = (int)(blocks_needed < cap ? blocks_needed : cap);
     size_t smem = sizeof(int)*OTB_NMSG*out->nt;
+#define OTB_LAUNCH_STORE(POL, CAPS) do { \
+        int blocks = otb_one_wave_grid(trace_store_kernel<POL, CAPS>, threads, smem, sm_count, blocks_needed); \
+        trace_store_kernel<POL, CAPS><<<blocks, threads, smem, stream>>>(a); } while (0)
 #if OTB_SPEC
     if (!otb_scene_equal(scene->k, K_SPEC_HOST)) {
         otb_set_error("this engine build is specialised for a different scene");
         return OTB_ERR_INVALID_ARG;
     }
-    trace_store_kernel<(OTB_SPEC_POL != 0), OTB_SPEC_CAPS><<<blocks, threads, smem, stream>>>(a);
+    OTB_LAUNCH_STORE((OTB_SPEC_POL != 0), OTB_SPEC_CAPS);
 #else
     const bool lean = scene->caps == OTB_CAPS_LENS;
     if (scene->k.no_pol) {
-        if (lean) trace_store_kernel<false, OTB_CAPS_LENS><<<blocks, threads, smem, stream>>>(a);
-        else trace_store_kernel<false, OTB_CAPS_FULL><<<blocks, threads, smem, stream>>>(a);
+        if (lean) OTB_LAUNCH_STORE(false, OTB_CAPS_LENS);
+        else OTB_LAUNCH_STORE(false, OTB_CAPS_FULL);
     } else {
-        if (lean) trace_store_kernel<true, OTB_CAPS_LENS><<<blocks, threads, smem, stream>>>(a);
-        else trace_store_kernel<true, OTB_CAPS_FULL><<<blocks, threads, smem, stream>>>(a);
+        if (lean) OTB_LAUNCH_STORE(true, OTB_CAPS_LENS);
+        else OTB_LAUNCH_STORE(true, OTB_CAPS_FULL);
     }
 #endif
     cudaError_t e = cudaGetLastError();

@@ -27,16 +27,14 @@ __device__ __forceinline__ bool bin_index(const BinGrid& g, double x, double y, 
 // summed by a rank-ordered tree reduction inside the peer group, and only the group leader issues the fp64
 // red.global.add atomics.  PSF-like images (double Gauss: 7 M hits in 3e4 pixels, 2e5 in the hottest one)
 // otherwise serialise on a handful of L2 addresses; spread images skip the reduction after one vote.
-__device__ __forceinline__ void accumulate_hit_warp(const BinGrid& g, const double* __restrict__ obs, bool ok, double x, double y,
-                                                    float w, float wl, double* __restrict__ img, int* __restrict__ cnt)
+__device__ __forceinline__ void accumulate_xyz_warp(const BinGrid& g, bool ok, double x, double y, float w,
+                                                    double ox, double oy, double oz, double* __restrict__ img, int* __restrict__ cnt)
 {
     const unsigned lane = threadIdx.x & 31;
     int xi = 0, yi = 0;
     ok = ok && bin_index(g, x, y, xi, yi);
     double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
     if (ok) {
-        double ox, oy, oz;
-        observer_xyz(obs, (double)wl, ox, oy, oz);
         const double wd = (double)w;
         v0 = ox*wd;
         v1 = oy*wd;
@@ -75,4 +73,13 @@ __device__ __forceinline__ void accumulate_hit_warp(const BinGrid& g, const doub
         atomicAdd(q + 3, v3);
         if (cnt) atomicAdd(cnt + pix, n);
     }
+}
+
+// same with the CIE observer lookup for the hit's wavelength
+__device__ __forceinline__ void accumulate_hit_warp(const BinGrid& g, const double* __restrict__ obs, bool ok, double x, double y,
+                                                    float w, float wl, double* __restrict__ img, int* __restrict__ cnt)
+{
+    double ox = 0.0, oy = 0.0, oz = 0.0;
+    if (ok) observer_xyz(obs, (double)wl, ox, oy, oz);
+    accumulate_xyz_warp(g, ok, x, y, w, ox, oy, oz, img, cnt);
 }

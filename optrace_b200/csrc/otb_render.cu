@@ -80,6 +80,10 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
     for (int i = threadIdx.x; i < OTB_NMSG*nt; i += blockDim.x) smsgs[i] = 0;
     __syncthreads();
 
+    // range mode: running hit ranges of this thread, merged into the global ranges once at the end of the kernel
+    double rg[OTB_MAX_DET][4];
+    for (int d = 0; d < OTB_MAX_DET; ++d) { rg[d][0] = INFINITY; rg[d][1] = -INFINITY; rg[d][2] = INFINITY; rg[d][3] = -INFINITY; }
+
     for (int64_t base = (int64_t)blockIdx.x*blockDim.x; base < N; base += (int64_t)gridDim.x*blockDim.x) {
         const int64_t ray = base + threadIdx.x;
         const bool valid = ray < N;
@@ -140,15 +144,21 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
             trace_step<POL, CAPS>(sc, aux, st, r, fl, za, zb, a.status);
             book_step(smsgs, nt, i, valid, fl);
 
-            // detector walk over section i = (p_i -> r.p)
+            // detector walk over section i = (p_i -> r.p); the segment direction is shared by all detectors
+            bool need = false;
             for (int d = 0; d < NDET; ++d) {
                 const KSurface& D = a.dets[d].surf;
                 const bool bmin = r.p.z >= D.z_min, bmax = r.p.z >= D.z_max;
                 ds[d].all_start = ds[d].all_start && (bmin && bmax);
                 ds[d].all_noreach = ds[d].all_noreach && (!bmin && !bmax);
                 if (!ds[d].started && bmin) ds[d].started = true;     // section before the first point behind z_min
-                if (valid && ds[d].started && !ds[d].finished) {
-                    const V3 sd = unit3(v3(r.p.x - p_i.x, r.p.y - p_i.y, r.p.z - p_i.z));
+                need = need || (valid && ds[d].started && !ds[d].finished);
+            }
+            if (!need) continue;
+            const V3 sd = unit3(v3(r.p.x - p_i.x, r.p.y - p_i.y, r.p.z - p_i.z));
+            for (int d = 0; d < NDET; ++d) {
+                const KSurface& D = a.dets[d].surf;
+                if (ds[d].started && !ds[d].finished) {
                     HitResult h = surf_find_hit<CAPS>(D, nullptr, p_i, sd, a.status);
                     if (!(h.p.z > r.p.z + OTB_C_EPS)) {
                         ds[d].finished = true;
@@ -166,6 +176,8 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
         }
 
         // rays still walking at the last stored point have no further section: no hit (raytracer.py:970-978)
+        double ox = 0.0, oy = 0.0, oz = 0.0;
+        if (a.mode == 0) observer_xyz(a.obs, (double)r.wl, ox, oy, oz);      // one observer lookup per ray
         for (int d = 0; d < NDET; ++d) {
             bool ok = valid && ds[d].ok && !(ds[d].all_start || ds[d].all_noreach);
             const RenderDet& rd = a.dets[d];
@@ -174,23 +186,31 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
                 ok = (e[0] <= ds[d].X) && (ds[d].X <= e[1]) && (e[2] <= ds[d].Y) && (ds[d].Y <= e[3]);
             }
             if (a.mode == 0) {
-                accumulate_hit_warp(rd.grid, a.obs, ok, ds[d].X, ds[d].Y, ds[d].w, r.wl, rd.img, rd.cnt);
-            } else {
-                double mnx = ok ? ds[d].X : INFINITY, mxx = ok ? ds[d].X : -INFINITY;
-                double mny = ok ? ds[d].Y : INFINITY, mxy = ok ? ds[d].Y : -INFINITY;
+                accumulate_xyz_warp(rd.grid, ok, ds[d].X, ds[d].Y, ds[d].w, ox, oy, oz, rd.img, rd.cnt);
+            } else if (ok) {
+                rg[d][0] = fmin(rg[d][0], ds[d].X);
+                rg[d][1] = fmax(rg[d][1], ds[d].X);
+                rg[d][2] = fmin(rg[d][2], ds[d].Y);
+                rg[d][3] = fmax(rg[d][3], ds[d].Y);
+            }
+        }
+    }
+
+    if (a.mode != 0) {
+        for (int d = 0; d < NDET; ++d) {
+            double mnx = rg[d][0], mxx = rg[d][1], mny = rg[d][2], mxy = rg[d][3];
 #pragma unroll
-                for (int k = 16; k > 0; k >>= 1) {
-                    mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, k));
-                    mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, k));
-                    mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, k));
-                    mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, k));
-                }
-                if ((threadIdx.x & 31) == 0 && mnx <= mxx) {
-                    atomic_min_dd(&rd.range[0], mnx);
-                    atomic_max_dd(&rd.range[1], mxx);
-                    atomic_min_dd(&rd.range[2], mny);
-                    atomic_max_dd(&rd.range[3], mxy);
-                }
+            for (int k = 16; k > 0; k >>= 1) {
+                mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, k));
+                mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, k));
+                mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, k));
+                mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, k));
+            }
+            if ((threadIdx.x & 31) == 0 && mnx <= mxx) {
+                atomic_min_dd(&a.dets[d].range[0], mnx);
+                atomic_max_dd(&a.dets[d].range[1], mxx);
+                atomic_min_dd(&a.dets[d].range[2], mny);
+                atomic_max_dd(&a.dets[d].range[3], mxy);
             }
         }
     }

@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--engine", default="generic", choices=["generic", "specialised"],
+                    help="trace kernel build: generic (scene in the constant bank, rolled step loop) or the "
+                         "scene-specialised variant of Raytracer.compile()")
+    ap.add_argument("--no-compare", action="store_true", help="skip timing the other engine build")
     return ap.parse_args()
 
 
@@ -196,7 +200,10 @@ def run_gpu(args):
         RT = scenes.double_gauss(ot)
     ot.global_options.show_warnings = False
     nt = len(RT.tracing_surfaces) + 2
-    specialised = RT.compile()      # scene-specialised trace kernel (in-tree cache, built by __graft_entry__.build())
+    # generic kernels by default; --engine specialised selects the scene-specialised build of Raytracer.compile()
+    # (in-tree cache, built by __graft_entry__.build())
+    RT.use_specialised_kernels = args.engine == "specialised"
+    specialised = RT.compile() if args.engine == "specialised" else False
 
     def barrier():
         if world > 1:
@@ -249,19 +256,22 @@ def run_gpu(args):
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kt]))
     power = img.power()
 
-    # for transparency: the same trace with the generic (not scene-specialised) kernel
-    generic_ms = None
-    if specialised:
-        RT.use_specialised_kernels = False
+    # for transparency: the same trace with the other engine build
+    other_ms = None
+    if not args.no_compare:
+        RT.use_specialised_kernels = not specialised
         RT._scene, RT._scene_key = None, None
+        if RT.use_specialised_kernels:
+            RT.compile()
         kt.clear()
         for k in range(4):
             step_resident(k > 0)
         torch.cuda.synchronize()
-        generic_ms = float(np.mean([a.elapsed_time(b) for a, b in kt]))
-        RT.use_specialised_kernels = True
+        other_ms = float(np.mean([a.elapsed_time(b) for a, b in kt]))
+        RT.use_specialised_kernels = specialised
         RT._scene, RT._scene_key = None, None
-        RT.compile()
+        if specialised:
+            RT.compile()
 
     # ---- end-to-end step through the public API: uploads + trace + image + D2H of the image ----
     del RT.check_if_rays_are_current
@@ -319,7 +329,8 @@ def run_gpu(args):
                        "parallelism": f"ray-sharded x{world}, all-reduce of image/extent/messages only",
                        "engine": ("scene-specialised trace kernel (Raytracer.compile(), cached nvcc build)" if specialised
                                   else "generic trace kernel"),
-                       "trace_kernel_ms": kernel_ms, "generic_trace_kernel_ms": generic_ms, "trace_only_ray_surfaces_per_s": n_local*world*(nt - 1)/(kernel_ms*1e-3),
+                       "trace_kernel_ms": kernel_ms,
+                       ("generic_trace_kernel_ms" if specialised else "specialised_trace_kernel_ms"): other_ms, "trace_only_ray_surfaces_per_s": n_local*world*(nt - 1)/(kernel_ms*1e-3),
                        "image_power_W": power},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved/peak_gbs,
                          "traffic": None, "kernel": "trace_store_kernel<POL>", "peak_source": peak_src,

@@ -63,6 +63,62 @@ __device__ __forceinline__ void atomic_max_dd(double* addr, double v)
     } while (assumed != old);
 }
 
+// one sequential step of the fused mode: trace, book messages, then the detector walk of _hit_detector
+// (raytracer.py:881-1051) online on section i = (p_i -> r.p) while it is still in registers
+template <bool POL, int CAPS>
+__device__ __forceinline__ void render_step(const KScene& sc, const RenderArgs& a, const int i, RayState& r, DetState* ds,
+                                            int* smsgs, const bool valid, const int64_t ray)
+{
+    const int64_t N = a.in.N;
+    const int NDET = a.n_det;
+    const OtbStep& st = sc.steps[i];
+    double za = 0.0, zb = 0.0;
+    if (CAPS == OTB_CAPS_FULL && st.hurb && valid) {
+        if (a.in.hurb_z_d) {
+            za = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 0)*N + ray];
+            zb = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 1)*N + ray];
+        } else {
+            Philox4 rnd = philox4x32_10((uint64_t)(a.in.ray_offset + ray), 0x48555242u, (uint32_t)st.hurb_slot, a.in.seed);
+            normal2(rnd, za, zb);
+        }
+    }
+    const V3 p_i = r.p;
+    const float w_i = r.w;
+    StepFlags fl;
+    trace_step<POL, CAPS>(sc, a.sc.aux, st, r, fl, za, zb, a.status);
+    book_step(smsgs, a.nt, i, valid, fl);
+
+    // the segment direction is shared by all detectors
+    bool need = false;
+    for (int d = 0; d < NDET; ++d) {
+        const KSurface& D = a.dets[d].surf;
+        const bool bmin = r.p.z >= D.z_min, bmax = r.p.z >= D.z_max;
+        ds[d].all_start = ds[d].all_start && (bmin && bmax);
+        ds[d].all_noreach = ds[d].all_noreach && (!bmin && !bmax);
+        if (!ds[d].started && bmin) ds[d].started = true;     // section before the first point behind z_min
+        need = need || (valid && ds[d].started && !ds[d].finished);
+    }
+    if (!need) return;
+    const V3 sd = unit3(v3(r.p.x - p_i.x, r.p.y - p_i.y, r.p.z - p_i.z));
+    for (int d = 0; d < NDET; ++d) {
+        const KSurface& D = a.dets[d].surf;
+        if (ds[d].started && !ds[d].finished) {
+            HitResult h = surf_find_hit<CAPS>(D, nullptr, p_i, sd, a.status);
+            if (!(h.p.z > r.p.z + OTB_C_EPS)) {
+                ds[d].finished = true;
+                if (h.hit && w_i > 0.0f) {
+                    double X = h.p.x, Y = h.p.y;
+                    sphere_project(D, a.dets[d].projection, X, Y, h.p.z);
+                    ds[d].X = X;
+                    ds[d].Y = Y;
+                    ds[d].w = w_i;
+                    ds[d].ok = true;
+                }
+            }
+        }
+    }
+}
+
 template <bool POL, int CAPS>
 __global__ void __launch_bounds__(OTB_RENDER_THREADS, OTB_MINBLOCKS(CAPS))
 trace_render_kernel(const __grid_constant__ RenderArgs a)
@@ -122,58 +178,11 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
         }
 
 #if OTB_SPEC
-#pragma unroll
-        for (int i = 0; i < OTB_SPEC_NSTEPS; ++i) {
+#define OTB_CALL_RENDER_STEP(i) render_step<POL, CAPS>(sc, a, i, r, ds, smsgs, valid, ray);
+        OTB_SPEC_FOREACH_STEP(OTB_CALL_RENDER_STEP)      // straight-line code, see otb_trace.cu
 #else
-        for (int i = 0; i < sc.n_steps; ++i) {
+        for (int i = 0; i < sc.n_steps; ++i) render_step<POL, CAPS>(sc, a, i, r, ds, smsgs, valid, ray);
 #endif
-            const OtbStep& st = sc.steps[i];
-            double za = 0.0, zb = 0.0;
-            if (CAPS == OTB_CAPS_FULL && st.hurb && valid) {
-                if (a.in.hurb_z_d) {
-                    za = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 0)*N + ray];
-                    zb = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 1)*N + ray];
-                } else {
-                    Philox4 rnd = philox4x32_10((uint64_t)(a.in.ray_offset + ray), 0x48555242u, (uint32_t)st.hurb_slot, a.in.seed);
-                    normal2(rnd, za, zb);
-                }
-            }
-            const V3 p_i = r.p;
-            const float w_i = r.w;
-            StepFlags fl;
-            trace_step<POL, CAPS>(sc, aux, st, r, fl, za, zb, a.status);
-            book_step(smsgs, nt, i, valid, fl);
-
-            // detector walk over section i = (p_i -> r.p); the segment direction is shared by all detectors
-            bool need = false;
-            for (int d = 0; d < NDET; ++d) {
-                const KSurface& D = a.dets[d].surf;
-                const bool bmin = r.p.z >= D.z_min, bmax = r.p.z >= D.z_max;
-                ds[d].all_start = ds[d].all_start && (bmin && bmax);
-                ds[d].all_noreach = ds[d].all_noreach && (!bmin && !bmax);
-                if (!ds[d].started && bmin) ds[d].started = true;     // section before the first point behind z_min
-                need = need || (valid && ds[d].started && !ds[d].finished);
-            }
-            if (!need) continue;
-            const V3 sd = unit3(v3(r.p.x - p_i.x, r.p.y - p_i.y, r.p.z - p_i.z));
-            for (int d = 0; d < NDET; ++d) {
-                const KSurface& D = a.dets[d].surf;
-                if (ds[d].started && !ds[d].finished) {
-                    HitResult h = surf_find_hit<CAPS>(D, nullptr, p_i, sd, a.status);
-                    if (!(h.p.z > r.p.z + OTB_C_EPS)) {
-                        ds[d].finished = true;
-                        if (h.hit && w_i > 0.0f) {
-                            double X = h.p.x, Y = h.p.y;
-                            sphere_project(D, a.dets[d].projection, X, Y, h.p.z);
-                            ds[d].X = X;
-                            ds[d].Y = Y;
-                            ds[d].w = w_i;
-                            ds[d].ok = true;
-                        }
-                    }
-                }
-            }
-        }
 
         // rays still walking at the last stored point have no further section: no hit (raytracer.py:970-978)
         double ox = 0.0, oy = 0.0, oz = 0.0;

@@ -22,6 +22,8 @@ struct StepFlags {
 
 #define OTB_INV_SQRT2 (1.0/1.4142135623730951)   // 1/np.sqrt(2)
 
+#include "otb_fast.cuh"
+
 // Raytracer.__compute_polarization (raytracer.py:831-879): returns amplitude components and writes the
 // new polarisation when the direction changed.
 template <bool POL>
@@ -91,8 +93,8 @@ __device__ __forceinline__ void hurb_props(const KSurface& S, double x, double y
 // One sequential step.  On entry `r` holds section i, on exit section i+1 (p, w, pol, n) and the new direction.
 // za, zb: standard normal deviates for HURB (only read when the step bends rays).
 template <bool POL, int CAPS>
-__device__ __forceinline__ void trace_step(const KScene& sc, const double* __restrict__ aux, const OtbStep& st, RayState& r,
-                                           StepFlags& fl, double za, double zb, int* status)
+__device__ __forceinline__ void trace_step_full(const KScene& sc, const double* __restrict__ aux, const OtbStep& st, RayState& r,
+                                                StepFlags& fl, double za, double zb, int* status)
 {
     const KSurface& S = sc.surf[st.surface];
     fl.ill = fl.absorb_missing = fl.tir = fl.outline = fl.hurb_neg = false;
@@ -217,6 +219,42 @@ __device__ __forceinline__ void trace_step(const KScene& sc, const double* __res
     }
 }
 
+// out-of-line copy of the full step for the rays the branch-free main path hands back (one copy per kernel, not
+// one per unrolled step).  State travels by value so that the caller's copy stays in registers on the main path.
+struct StepIO {
+    RayState r;
+    StepFlags fl;
+};
+
+template <bool POL, int CAPS>
+__device__ __noinline__ StepIO trace_step_slow(const KScene* sc, const double* aux, const OtbStep* st, RayState r, int* status)
+{
+    StepIO o;
+    o.r = r;
+    trace_step_full<POL, CAPS>(*sc, aux, *st, o.r, o.fl, 0.0, 0.0, status);
+    return o;
+}
+
+// One sequential step: spherical lens surfaces take the branch-free main path (otb_fast.cuh) and fall back to
+// the full step per ray; everything else runs the full step.
+template <bool POL, int CAPS>
+__device__ __forceinline__ void trace_step(const KScene& sc, const double* __restrict__ aux, const OtbStep& st, RayState& r,
+                                           StepFlags& fl, double za, double zb, int* status)
+{
+#ifndef OTB_NO_FAST_PATH
+    const KSurface& S = sc.surf[st.surface];
+    if (st.role <= OTB_STEP_LENS_BACK && S.kind == OTB_SURF_CONIC && S.par[OTB_P_K] == 0.0) {
+        if (!fast_sphere_lens_step<POL>(sc, st, S, r, fl, status)) {
+            const StepIO o = trace_step_slow<POL, CAPS>(&sc, aux, &st, r, status);
+            r = o.r;
+            fl = o.fl;
+        }
+        return;
+    }
+#endif
+    trace_step_full<POL, CAPS>(sc, aux, st, r, fl, za, zb, status);
+}
+
 // warp-aggregated message booking: one shared-memory atomic per warp and message type; the common case
 // (no message in the whole warp) costs one vote
 __device__ __forceinline__ void book(int* smsgs, int slot, bool pred)
@@ -254,5 +292,8 @@ static const KScene K_SPEC_HOST = OTB_SPEC_SCENE_INIT;
 #if OTB_SPEC && defined(OTB_SPEC_MINBLOCKS)
 #define OTB_MINBLOCKS(CAPS) OTB_SPEC_MINBLOCKS
 #else
-#define OTB_MINBLOCKS(CAPS) ((CAPS) == OTB_CAPS_LENS ? 4 : 3)
+#ifndef OTB_LENS_MINBLOCKS
+#define OTB_LENS_MINBLOCKS 4
+#endif
+#define OTB_MINBLOCKS(CAPS) ((CAPS) == OTB_CAPS_LENS ? OTB_LENS_MINBLOCKS : 3)
 #endif

@@ -20,6 +20,56 @@ struct TraceArgs {
     int* status;
 };
 
+struct StoreCursor {
+    double* pp;     // p plane x of the current section (y, z at +N*nt, +2*N*nt)
+    float* pw;
+    double* pn;
+    float* ppol;
+};
+
+// one sequential step: trace, book messages, store section i+1
+template <bool POL, int CAPS>
+__device__ __forceinline__ void store_step(const KScene& sc, const TraceArgs& a, const int i, RayState& r, StoreCursor& c,
+                                           int* smsgs, const bool valid, const int64_t rr)
+{
+    const int64_t N = a.out.N;
+    const int nt = a.out.nt;
+    const int64_t Nnt = N*(int64_t)nt;
+    const OtbStep& st = sc.steps[i];
+    double za = 0.0, zb = 0.0;
+    if (CAPS == OTB_CAPS_FULL && st.hurb) {
+        if (a.in.hurb_z_d) {
+            za = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 0)*N + rr];
+            zb = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 1)*N + rr];
+        } else {
+            Philox4 rnd = philox4x32_10((uint64_t)(a.in.ray_offset + rr), 0x48555242u, (uint32_t)st.hurb_slot, a.in.seed);
+            normal2(rnd, za, zb);
+        }
+    }
+    StepFlags fl;
+    trace_step<POL, CAPS>(sc, a.sc.aux, st, r, fl, za, zb, a.status);
+    book_step(smsgs, nt, i, valid, fl);
+
+    c.pp += N;
+    c.pw += N;
+    c.pn += N;
+    if (valid) {
+        __stcs(c.pp, r.p.x);
+        __stcs(c.pp + Nnt, r.p.y);
+        __stcs(c.pp + 2*Nnt, r.p.z);
+        __stcs(c.pw, r.w);
+        __stcs(c.pn, r.n);
+    }
+    if (POL) {
+        c.ppol += N;
+        if (valid) {
+            __stcs(c.ppol, r.pol[0]);
+            __stcs(c.ppol + Nnt, r.pol[1]);
+            __stcs(c.ppol + 2*Nnt, r.pol[2]);
+        }
+    }
+}
+
 template <bool POL, int CAPS>
 __global__ void __launch_bounds__(OTB_TRACE_THREADS, OTB_MINBLOCKS(CAPS))
 trace_store_kernel(const __grid_constant__ TraceArgs a)
@@ -58,10 +108,15 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
         if (valid && r.n < 1.0) atomicOr(a.status, OTB_STATUS_NBELOW1);
 
         // running plane pointers: one add per plane and section instead of 64-bit index arithmetic
-        double* pp = a.out.p_d + rr;
-        float* pw = a.out.w_d + rr;
-        double* pn = a.out.n_d + rr;
-        float* ppol = POL ? a.out.pol_d + rr : nullptr;
+        StoreCursor cur;
+        cur.pp = a.out.p_d + rr;
+        cur.pw = a.out.w_d + rr;
+        cur.pn = a.out.n_d + rr;
+        cur.ppol = POL ? a.out.pol_d + rr : nullptr;
+        double* const pp = cur.pp;
+        float* const pw = cur.pw;
+        double* const pn = cur.pn;
+        float* const ppol = cur.ppol;
 
         if (valid) {
             __stcs(pp, r.p.x);
@@ -78,45 +133,13 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
         }
 
 #if OTB_SPEC
-#pragma unroll
-        for (int i = 0; i < OTB_SPEC_NSTEPS; ++i) {
+        // straight-line code: one inlined copy of store_step per literal step index, everything about the step
+        // (role, surface kind and parameters, media) folds at compile time
+#define OTB_CALL_STORE_STEP(i) store_step<POL, CAPS>(sc, a, i, r, cur, smsgs, valid, rr);
+        OTB_SPEC_FOREACH_STEP(OTB_CALL_STORE_STEP)
 #else
-        for (int i = 0; i < sc.n_steps; ++i) {
+        for (int i = 0; i < sc.n_steps; ++i) store_step<POL, CAPS>(sc, a, i, r, cur, smsgs, valid, rr);
 #endif
-            const OtbStep& st = sc.steps[i];
-            double za = 0.0, zb = 0.0;
-            if (CAPS == OTB_CAPS_FULL && st.hurb) {
-                if (a.in.hurb_z_d) {
-                    za = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 0)*N + rr];
-                    zb = a.in.hurb_z_d[((int64_t)st.hurb_slot*2 + 1)*N + rr];
-                } else {
-                    Philox4 rnd = philox4x32_10((uint64_t)(a.in.ray_offset + rr), 0x48555242u, (uint32_t)st.hurb_slot, a.in.seed);
-                    normal2(rnd, za, zb);
-                }
-            }
-            StepFlags fl;
-            trace_step<POL, CAPS>(sc, aux, st, r, fl, za, zb, a.status);
-            book_step(smsgs, nt, i, valid, fl);
-
-            pp += N;
-            pw += N;
-            pn += N;
-            if (valid) {
-                __stcs(pp, r.p.x);
-                __stcs(pp + Nnt, r.p.y);
-                __stcs(pp + 2*Nnt, r.p.z);
-                __stcs(pw, r.w);
-                __stcs(pn, r.n);
-            }
-            if (POL) {
-                ppol += N;
-                if (valid) {
-                    __stcs(ppol, r.pol[0]);
-                    __stcs(ppol + Nnt, r.pol[1]);
-                    __stcs(ppol + 2*Nnt, r.pol[2]);
-                }
-            }
-        }
         if (valid) {
             __stcs(&a.out.s_d[rr], r.s.x);
             __stcs(&a.out.s_d[rr + N], r.s.y);

@@ -47,7 +47,10 @@ def _source_digest() -> str:
 def build_library(out_path=None, extra_flags=(), force=False, objdir=None, sources=None, extra_objects=()) -> pathlib.Path:
     """Compiles the engine sources in parallel and links a shared library."""
     out_path = pathlib.Path(out_path) if out_path else CSRC / "libotb.so"
-    objdir = pathlib.Path(objdir) if objdir else CSRC / "build"
+    base_build = objdir is None
+    # variant builds get a private object directory per process: several ranks (torchrun) or threads may miss the
+    # cache for the same variant at the same time; the finished library is moved into place atomically
+    objdir = CSRC / "build" if base_build else pathlib.Path(f"{objdir}.{os.getpid()}")
     objdir.mkdir(parents=True, exist_ok=True)
     stamp = objdir / (out_path.name + ".digest")
     digest = source_digest() + "|" + " ".join(extra_flags)
@@ -66,10 +69,16 @@ def build_library(out_path=None, extra_flags=(), force=False, objdir=None, sourc
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(compile_one, srcs))
-    r = subprocess.run([cc, "-shared", "-o", str(out_path), *[str(o) for o in objs], *[str(o) for o in extra_objects],
+    tmp_out = out_path.with_name(f".{out_path.name}.{os.getpid()}.tmp")
+    r = subprocess.run([cc, "-shared", "-o", str(tmp_out), *[str(o) for o in objs], *[str(o) for o in extra_objects],
                         "-lcudart"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    stamp.write_text(digest)
+    os.replace(tmp_out, out_path)
+    if base_build:
+        stamp.write_text(digest)
+    else:
+        import shutil
+        shutil.rmtree(objdir, ignore_errors=True)
     return out_path

@@ -287,7 +287,6 @@ def build_specialised_library(user_funcs, api_only: bool = False) -> pathlib.Pat
     """engine variant with the given user callables compiled in; cached by header + engine source hash.
     api_only: only the array entry points (Surface.find_hit / normals / values on a stand-alone surface) see the
     callables; the trace kernels are linked from the base build (much faster to compile)."""
-    import shutil
     header = generate_header(user_funcs)
     key = hashlib.sha256((header + build.source_digest() + ("api" if api_only else "")).encode()).hexdigest()[:16]
     JIT_DIR.mkdir(parents=True, exist_ok=True)
@@ -302,5 +301,4 @@ def build_specialised_library(user_funcs, api_only: bool = False) -> pathlib.Pat
     keep = ("otb_api.cu",) if api_only else ("otb_api.cu", "otb_trace.cu", "otb_render.cu")
     base_objs = [build.CSRC / "build" / f.replace(".cu", ".o") for f in build.SOURCES if f not in keep]
     build.build_library(lib, extra_flags=flags, force=True, objdir=objdir, sources=list(keep), extra_objects=base_objs)
-    shutil.rmtree(objdir, ignore_errors=True)
     return lib

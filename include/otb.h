@@ -307,6 +307,10 @@ int otb_stream_sync(void* stream);
  * Raytracer.__tracing_elements / sub_trace (raytracer.py:297-397, 492-508). */
 int otb_scene_create(const OtbSceneDesc* desc, OtbScene** out);
 int otb_scene_destroy(OtbScene* scene);
+/* Re-sends a descriptor of the same shape (same aux table size) into an existing scene: host record refreshed,
+ * aux tables copied asynchronously on `stream`, no allocation and no device synchronisation.  For callers that
+ * re-upload the scene at every trace (the reference re-walks its object tree per trace, raytracer.py:297-305). */
+int otb_scene_update(OtbScene* scene, const OtbSceneDesc* desc, void* stream);
 
 /* Store-mode trace: replaces Raytracer.trace's sub_trace surface loop (raytracer.py:297-397)
  * including find_hit, __refraction, __compute_polarization, __refraction_ideal_lens, __hurb,

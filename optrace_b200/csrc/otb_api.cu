@@ -112,9 +112,8 @@ static bool scene_needs_user_funcs(const OtbSceneDesc* d)
     return false;
 }
 
-int otb_scene_create(const OtbSceneDesc* d, OtbScene** out)
+static int check_scene_desc(const OtbSceneDesc* d)
 {
-    if (!d || !out) { otb_set_error("null argument"); return OTB_ERR_INVALID_ARG; }
     if (d->abi_version != OTB_ABI_VERSION) { otb_set_error("ABI version mismatch"); return OTB_ERR_INVALID_ARG; }
     if (d->n_steps < 1 || d->n_surfaces < 1 || d->n_media < 1) { otb_set_error("empty scene"); return OTB_ERR_INVALID_ARG; }
     for (int i = 0; i < d->n_steps; ++i) {
@@ -134,9 +133,14 @@ int otb_scene_create(const OtbSceneDesc* d, OtbScene** out)
                       OTB_MAX_STEPS, OTB_MAX_MEDIA, OTB_MAX_FILTERS);
         return OTB_ERR_UNSUPPORTED;
     }
-    OtbScene* sc = new OtbScene();
-    memset(sc, 0, sizeof(*sc));
+    return OTB_OK;
+}
+
+// host-side kernel-parameter scene (KScene) and capability level from a descriptor
+static void fill_kscene(const OtbSceneDesc* d, OtbScene* sc)
+{
     KScene& k = sc->k;
+    memset(&k, 0, sizeof(k));
     k.n_steps = d->n_steps;
     k.n_media = d->n_media;
     k.n_filters = d->n_filters;
@@ -149,14 +153,6 @@ int otb_scene_create(const OtbSceneDesc* d, OtbScene** out)
     for (int i = 0; i < d->n_surfaces; ++i) k.surf[i] = otb_ksurface(d->surfaces[i]);
     for (int i = 0; i < d->n_media; ++i) k.media[i] = d->media[i];
     for (int i = 0; i < d->n_filters; ++i) k.filters[i] = d->filters[i];
-    const size_t naux = d->n_aux > 0 ? (size_t)d->n_aux : 1;
-    cudaError_t e = cudaMalloc(&sc->aux_d, sizeof(double)*naux);
-    if (e != cudaSuccess) { delete sc; return otb_cuda_fail(e, "cudaMalloc(scene aux)"); }
-    if (d->n_aux > 0) {
-        e = cudaMemcpy(sc->aux_d, d->aux, sizeof(double)*d->n_aux, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) { cudaFree(sc->aux_d); delete sc; return otb_cuda_fail(e, "cudaMemcpy(scene aux)"); }
-    }
-    k.aux = sc->aux_d;
     sc->nt = d->n_steps + 1;
     sc->caps = OTB_CAPS_LENS;
     for (int i = 0; i < d->n_surfaces; ++i) {
@@ -164,7 +160,37 @@ int otb_scene_create(const OtbSceneDesc* d, OtbScene** out)
         if (kd == OTB_SURF_TILTED || kd == OTB_SURF_ASPHERE || kd == OTB_SURF_FUNC || kd == OTB_SURF_DATA) sc->caps = OTB_CAPS_FULL;
     }
     for (int i = 0; i < d->n_steps; ++i) if (d->steps[i].hurb) sc->caps = OTB_CAPS_FULL;
+}
+
+int otb_scene_create(const OtbSceneDesc* d, OtbScene** out)
+{
+    if (!d || !out) { otb_set_error("null argument"); return OTB_ERR_INVALID_ARG; }
+    if (int rc = check_scene_desc(d)) return rc;
+    OtbScene* sc = new OtbScene();
+    memset(sc, 0, sizeof(*sc));
+    fill_kscene(d, sc);
+    const size_t naux = d->n_aux > 0 ? (size_t)d->n_aux : 1;
+    cudaError_t e = cudaMalloc(&sc->aux_d, sizeof(double)*naux);
+    if (e != cudaSuccess) { delete sc; return otb_cuda_fail(e, "cudaMalloc(scene aux)"); }
+    if (d->n_aux > 0) {
+        e = cudaMemcpy(sc->aux_d, d->aux, sizeof(double)*d->n_aux, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(sc->aux_d); delete sc; return otb_cuda_fail(e, "cudaMemcpy(scene aux)"); }
+    }
+    sc->n_aux = d->n_aux;
+    sc->k.aux = sc->aux_d;
     *out = sc;
+    return OTB_OK;
+}
+
+int otb_scene_update(OtbScene* sc, const OtbSceneDesc* d, void* stream)
+{
+    if (!sc || !d) { otb_set_error("null argument"); return OTB_ERR_INVALID_ARG; }
+    if (int rc = check_scene_desc(d)) return rc;
+    if (d->n_aux != sc->n_aux) { otb_set_error("aux table size changed: re-create the scene"); return OTB_ERR_INVALID_ARG; }
+    fill_kscene(d, sc);
+    sc->k.aux = sc->aux_d;
+    if (d->n_aux > 0)
+        OTB_CUDA(cudaMemcpyAsync(sc->aux_d, d->aux, sizeof(double)*d->n_aux, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return OTB_OK;
 }
 

@@ -22,18 +22,19 @@ __device__ __forceinline__ bool bin_index(const BinGrid& g, double x, double y, 
     return !((xi < 0) || (yi < 0) || (yi >= g.Ny) || (xi >= g.Nx));
 }
 
-// Warp-aggregated accumulation (must be called by all 32 lanes; `ok` marks lanes that carry a hit).
+// Warp-level aggregation (must be called by all 32 lanes; `ok` marks lanes that carry a hit).
 // Lanes whose hits fall into the same pixel are found with __match_any_sync, their four channel values are
-// summed by a rank-ordered tree reduction inside the peer group, and only the group leader issues the fp64
-// red.global.add atomics.  PSF-like images (double Gauss: 7 M hits in 3e4 pixels, 2e5 in the hottest one)
-// otherwise serialise on a handful of L2 addresses; spread images skip the reduction after one vote.
-__device__ __forceinline__ void accumulate_xyz_warp(const BinGrid& g, bool ok, double x, double y, float w,
-                                                    double ox, double oy, double oz, double* __restrict__ img, int* __restrict__ cnt)
+// summed by a rank-ordered tree reduction inside the peer group.  Returns true on the group leaders, which then
+// hold the pixel index, the channel sums and the hit count of their group.  PSF-like images (double Gauss: 7 M
+// hits in 3e4 pixels, 2e5 in the hottest one) otherwise serialise on a handful of addresses; spread images skip
+// the reduction after one vote.
+__device__ __forceinline__ bool aggregate_xyz_warp(const BinGrid& g, bool ok, double x, double y, float w,
+                                                   double ox, double oy, double oz, unsigned lane,
+                                                   double& v0, double& v1, double& v2, double& v3, int& n, int& pix)
 {
-    const unsigned lane = threadIdx.x & 31;
     int xi = 0, yi = 0;
     ok = ok && bin_index(g, x, y, xi, yi);
-    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    v0 = v1 = v2 = v3 = 0.0;
     if (ok) {
         const double wd = (double)w;
         v0 = ox*wd;
@@ -41,10 +42,10 @@ __device__ __forceinline__ void accumulate_xyz_warp(const BinGrid& g, bool ok, d
         v2 = oz*wd;
         v3 = wd;
     }
-    const int pix = ok ? yi*g.Nx + xi : -1 - (int)lane;          // lanes without a hit never share a key
+    pix = ok ? yi*g.Nx + xi : -1 - (int)lane;          // lanes without a hit never share a key
     const unsigned peers = __match_any_sync(0xffffffffu, pix);
     const int size = __popc(peers);
-    int n = ok ? 1 : 0;
+    n = ok ? 1 : 0;
     if (__any_sync(0xffffffffu, size > 1)) {
         const int rank = __popc(peers & ((1u << lane) - 1));
 #pragma unroll
@@ -65,6 +66,16 @@ __device__ __forceinline__ void accumulate_xyz_warp(const BinGrid& g, bool ok, d
         }
         ok = ok && rank == 0;
     }
+    return ok;
+}
+
+// aggregation + fp64 red.global.add atomics by the group leaders
+__device__ __forceinline__ void accumulate_xyz_warp(const BinGrid& g, bool ok, double x, double y, float w,
+                                                    double ox, double oy, double oz, double* __restrict__ img, int* __restrict__ cnt)
+{
+    double v0, v1, v2, v3;
+    int n, pix;
+    ok = aggregate_xyz_warp(g, ok, x, y, w, ox, oy, oz, threadIdx.x & 31, v0, v1, v2, v3, n, pix);
     if (ok) {
         double* q = img + 4*(int64_t)pix;
         atomicAdd(q + 0, v0);

@@ -62,20 +62,47 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x)
     return x;
 }
 
+__host__ __device__ __forceinline__ int bits_for(uint64_t n)      // smallest b with 2^b >= n (n >= 2)
+{
+#ifdef __CUDA_ARCH__
+    return 64 - __clzll((long long)(n - 1));
+#else
+    int bits = 0;
+    while (((uint64_t)1 << bits) < n) ++bits;
+    return bits;
+#endif
+}
+
 __host__ __device__ inline uint64_t feistel_perm(uint64_t i, uint64_t n, uint64_t key)
 {
     if (n <= 1) return 0;
-    int bits = 0;
-    while (((uint64_t)1 << bits) < n) ++bits;
+    int bits = bits_for(n);
     bits += bits & 1;                       // even number of bits
     const int half = bits >> 1;
     const uint32_t mask = (half >= 32) ? 0xffffffffu : (((uint32_t)1 << half) - 1);
+    const uint32_t ka = (uint32_t)key ^ (uint32_t)(key >> 32), kb = (uint32_t)(key >> 16) ^ (uint32_t)(key >> 32);
+    if (bits <= 32) {                       // all 32-bit arithmetic (every launch below 4 G rays per source)
+        uint32_t x = (uint32_t)i;
+        const uint32_t n32 = (uint32_t)(n - 1);
+        do {
+            uint32_t l = (x >> half) & mask, r = x & mask;
+#pragma unroll
+            for (int rd = 0; rd < 4; ++rd) {
+                uint32_t f = mix32(r ^ ((rd & 1) ? kb : ka) ^ (0x9E3779B9u*(rd + 1))) & mask;
+                uint32_t nl = r;
+                r = l ^ f;
+                l = nl;
+            }
+            x = (l << half) | r;
+        } while (x > n32);
+        return x;
+    }
     uint64_t x = i;
     do {
         uint32_t l = (uint32_t)(x >> half) & mask, r = (uint32_t)x & mask;
 #pragma unroll
         for (int rd = 0; rd < 4; ++rd) {
-            uint32_t f = mix32(r ^ (uint32_t)(key >> (16*(rd & 1))) ^ (0x9E3779B9u*(rd + 1)) ^ (uint32_t)(key >> 32)) & mask;
+            uint32_t f = mix32(r ^ ((rd & 1) ? kb : ka) ^ (0x9E3779B9u*(rd + 1))) & mask;
             uint32_t nl = r;
             r = l ^ f;
             l = nl;

@@ -24,6 +24,10 @@ struct StepFlags {
 
 #include "otb_fast.cuh"
 
+#ifndef OTB_STEP_OOL
+#define OTB_STEP_OOL 1
+#endif
+
 // Raytracer.__compute_polarization (raytracer.py:831-879): returns amplitude components and writes the
 // new polarisation when the direction changed.
 template <bool POL>
@@ -227,32 +231,47 @@ struct StepIO {
 };
 
 template <bool POL, int CAPS>
-__device__ __noinline__ StepIO trace_step_slow(const KScene* sc, const double* aux, const OtbStep* st, RayState r, int* status)
+__device__ __noinline__ StepIO trace_step_slow(const KScene* sc, const double* aux, const OtbStep* st, RayState r,
+                                               double za, double zb, int* status)
 {
     StepIO o;
     o.r = r;
-    trace_step_full<POL, CAPS>(*sc, aux, *st, o.r, o.fl, 0.0, 0.0, status);
+    trace_step_full<POL, CAPS>(*sc, aux, *st, o.r, o.fl, za, zb, status);
     return o;
 }
 
 // One sequential step: spherical lens surfaces take the branch-free main path (otb_fast.cuh) and fall back to
-// the full step per ray; everything else runs the full step.
+// the full step per ray; everything else runs the full step.  With OTB_STEP_OOL the full step exists only as
+// the out-of-line copy: the step loop then holds the straight-line path and ONE call site, which keeps the
+// loop-carried ray state in fixed registers (no copies where the paths merge) and the hot loop small.
 template <bool POL, int CAPS>
 __device__ __forceinline__ void trace_step(const KScene& sc, const double* __restrict__ aux, const OtbStep& st, RayState& r,
                                            StepFlags& fl, double za, double zb, int* status)
 {
 #ifndef OTB_NO_FAST_PATH
     const KSurface& S = sc.surf[st.surface];
+    bool done = false;
+    if (st.role <= OTB_STEP_LENS_BACK && S.kind == OTB_SURF_CONIC && S.par[OTB_P_K] == 0.0)
+        done = fast_sphere_lens_step<POL>(sc, st, S, r, fl, status);
+#if OTB_STEP_OOL
+    if (!done) {
+        const StepIO o = trace_step_slow<POL, CAPS>(&sc, aux, &st, r, za, zb, status);
+        r = o.r;
+        fl = o.fl;
+    }
+#else
+    if (done) return;
     if (st.role <= OTB_STEP_LENS_BACK && S.kind == OTB_SURF_CONIC && S.par[OTB_P_K] == 0.0) {
-        if (!fast_sphere_lens_step<POL>(sc, st, S, r, fl, status)) {
-            const StepIO o = trace_step_slow<POL, CAPS>(&sc, aux, &st, r, status);
-            r = o.r;
-            fl = o.fl;
-        }
+        const StepIO o = trace_step_slow<POL, CAPS>(&sc, aux, &st, r, za, zb, status);
+        r = o.r;
+        fl = o.fl;
         return;
     }
-#endif
     trace_step_full<POL, CAPS>(sc, aux, st, r, fl, za, zb, status);
+#endif
+#else
+    trace_step_full<POL, CAPS>(sc, aux, st, r, fl, za, zb, status);
+#endif
 }
 
 // warp-aggregated message booking: one shared-memory atomic per warp and message type; the common case

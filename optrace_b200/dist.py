@@ -58,6 +58,26 @@ def allreduce_sum_(t):
     return t
 
 
+def allreduce_sum_async(tensors):
+    """SUM all-reduce of GPU tensors on the side stream, ordered after the work queued so far on the current
+    stream.  Returns the CUDA event that marks completion (None when there is nothing to reduce): the caller's
+    stream goes on with the next trace while NCCL moves the image over NVLink."""
+    if not (is_dist() and world() > 1):
+        return None
+    import torch
+    from . import engine
+    td = _td()
+    side = engine.side_stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for t in tensors:
+            td.all_reduce(t, op=td.ReduceOp.SUM)
+            t.record_stream(side)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    return ev
+
+
 def allreduce_range_(rng):
     """rng = [min x, max x, min y, max y] tensor: MIN/MAX all-reduce for the auto extent (raytracer.py:1042-1046)"""
     if is_dist() and world() > 1:

@@ -49,6 +49,36 @@ def stream_ptr():
     return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
 
 
+_side = {}
+
+
+def side_stream():
+    """per-device side stream: image all-reduces and device->host downloads run here, behind an event of the
+    compute stream, so that the next trace overlaps them"""
+    torch = _torch()
+    d = torch.cuda.current_device()
+    if d not in _side:
+        _side[d] = torch.cuda.Stream(device=d)
+    return _side[d]
+
+
+_pinned_pool = {}
+
+
+def pinned_take(shape, dtype):
+    """pinned host buffer from a small free list (page-locking 143 MB costs tens of ms)"""
+    torch = _torch()
+    key = (tuple(shape), dtype)
+    free = _pinned_pool.setdefault(key, [])
+    return free.pop() if free else torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+def pinned_give(buf):
+    free = _pinned_pool.setdefault((tuple(buf.shape), buf.dtype), [])
+    if len(free) < 3:
+        free.append(buf)
+
+
 def device():
     torch = _torch()
     return torch.device("cuda", torch.cuda.current_device())
@@ -96,12 +126,10 @@ class SceneHandle:
         self.nt = flat.nt
 
     def reupload(self):
-        """destroy and re-create the device copy of the (unchanged) flattened scene: host -> device again"""
-        self.lib.otb_scene_destroy(self.handle)
-        desc = self.flat.to_ctypes()
-        h = C.c_void_p()
-        check(self.lib.otb_scene_create(C.byref(desc), C.byref(h)), self.lib)
-        self.handle = h
+        """send the (unchanged) flattened scene host -> device again: otb_scene_update, asynchronous, no
+        allocation (a cudaFree here would synchronise the device and serialise the overlapped image download)"""
+        self._desc = self.flat.to_ctypes()          # kept alive until the asynchronous copy has been consumed
+        check(self.lib.otb_scene_update(self.handle, C.byref(self._desc), stream_ptr()), self.lib)
 
     def close(self):
         if getattr(self, "handle", None):
@@ -249,6 +277,9 @@ def raise_status(st: int):
 # ---------------------------------------------------------------------------------------------------
 # detector
 # ---------------------------------------------------------------------------------------------------
+_det_meta_template = {}
+
+
 def _det_struct(rec: dict) -> _cabi.OtbDetector:
     from .scene import fill_detector
     d = _cabi.OtbDetector()
@@ -265,14 +296,26 @@ def detector_hits(lib, store: DeviceStore, det_rec: dict, ray_begin: int = 0, ra
     hx = torch.empty(max(n, 1), dtype=torch.float64, device=d)
     hy = torch.empty(max(n, 1), dtype=torch.float64, device=d)
     hw = torch.empty(max(n, 1), dtype=torch.float32, device=d)
-    rng = torch.tensor([np.inf, -np.inf, np.inf, -np.inf], dtype=torch.float64, device=d)
-    ill = torch.zeros(1, dtype=torch.int64, device=d)
-    status = torch.zeros(1, dtype=torch.int32, device=d)
+    # one 48-byte scratch record [range(4) f64 | ill i64 | status i32] so that the caller reads everything back
+    # with a single device -> host copy; initialised from a cached device template (no host -> device copy)
+    key = d.index
+    if key not in _det_meta_template:
+        t = torch.zeros(6, dtype=torch.float64)
+        t[:4] = torch.tensor([np.inf, -np.inf, np.inf, -np.inf], dtype=torch.float64)
+        _det_meta_template[key] = t.to(d)
+    meta = _det_meta_template[key].clone()
+    rng, ill, status = meta[:4], meta[4:5].view(torch.int64), meta[5:6].view(torch.int32)[:1]
     s = store.c_struct()
     det = _det_struct(det_rec)
     check(lib.otb_detector_hits(C.byref(s), ray_begin, ray_end, C.byref(det), dptr(hx), dptr(hy), dptr(hw),
                                 dptr(rng), dptr(ill), dptr(status), stream_ptr()), lib)
-    return hx[:n], hy[:n], hw[:n], rng, ill, status
+    return hx[:n], hy[:n], hw[:n], rng, ill, status, meta
+
+
+def read_det_meta(meta):
+    """(range ndarray[4], ill count, status) from the scratch record of detector_hits: one synchronising copy"""
+    m = meta.cpu()
+    return m[:4].numpy().copy(), int(m[4:5].view(_torch().int64).item()), int(m[5:6].view(_torch().int32)[0].item())
 
 
 def render_xyzw(lib, x, y, w, wl, extent, Nx: int, Ny: int, img=None, cnt=None):

@@ -378,19 +378,20 @@ class Raytracer(Group):
         rec = detector_record(dsurf, projection_method, extent)
         b, e = self.rays._local_range(source_index)
         lib = self._scene.lib
-        hx, hy, hw, rng, ill, status = engine.detector_hits(lib, self.rays._dev, rec, b, e)
+        hx, hy, hw, rng, ill, status, meta = engine.detector_hits(lib, self.rays._dev, rec, b, e)
         dist.allreduce_sum_(ill)
         projection = projection_method if rec["projection"] else None
+        if extent is None:
+            dist.allreduce_range_(rng)
+        r, ill_count, st = engine.read_det_meta(meta)      # the one host synchronisation of this call
         if extent is not None:
             extent_out = np.asarray_chkfinite(np.array(extent, dtype=np.float64))
         else:
-            dist.allreduce_range_(rng)
-            r = rng.cpu().numpy()
             extent_out = self.detectors[detector_index].pos[:2].repeat(2)
             if r[0] <= r[1]:
                 extent_out = r.copy()
-        engine.raise_status(int(status.item()))
-        return hx, hy, hw, self.rays._dev.wl[b:e], extent_out, projection, int(ill.item())
+        engine.raise_status(st)
+        return hx, hy, hw, self.rays._dev.wl[b:e], extent_out, projection, ill_count
 
     def detector_image(self, detector_index: int = 0, source_index: int = None, extent=None, limit: float = None,
                        projection_method: str = "Equidistant", **kwargs) -> RenderImage:
@@ -409,9 +410,8 @@ class Raytracer(Group):
         img._fix_extent()
         Nx, Ny = img._grid()
         data, cnt = engine.render_xyzw(self._scene.lib, hx, hy, hw, wl, img.extent, Nx, Ny)
-        dist.allreduce_sum_(data)
-        dist.allreduce_sum_(cnt)
         img._data_dev, img._counts_dev = data, cnt
+        img._ready = dist.allreduce_sum_async((data, cnt)) if data.is_cuda else None     # side stream, NCCL
         if ill_count:
             warning(f"{ill_count} rays ({100*ill_count/self.rays.N_global:.3g}% of all rays) were ill-conditioned for "
                     f"numerical hit finding at detector {detector_index}. Where and whether they intersect might be wrong.")
@@ -450,9 +450,8 @@ class Raytracer(Group):
         img._fix_extent()
         Nx, Ny = img._grid()
         data, cnt = engine.render_xyzw(self._scene.lib, x, y, st.w[b:e], st.wl[b:e], img.extent, Nx, Ny)
-        dist.allreduce_sum_(data)
-        dist.allreduce_sum_(cnt)
         img._data_dev, img._counts_dev = data, cnt
+        img._ready = dist.allreduce_sum_async((data, cnt)) if data.is_cuda else None
         return img
 
     def source_spectrum(self, source_index: int = 0, **kwargs) -> LightSpectrum:

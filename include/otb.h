@@ -206,6 +206,8 @@ typedef struct OtbRayStore {
     float* w_d;      /* (N, nt) F-order */
     double* n_d;     /* (N, nt) F-order */
     float* wl_d;     /* (N) */
+    const int32_t* trace_status_d;   /* optional: status word of the trace that filled the store (device); when it
+                                        lacks OTB_STATUS_Z_DECREASE the detector search may bisect the sections */
 } OtbRayStore;
 
 /* ---- detectors (raytracer.py:881-1051, render_image.py:361-421) ------------------------- */
@@ -287,6 +289,7 @@ typedef struct OtbDeviceInfo {
 #define OTB_STATUS_TIMEOUT 1       /* Illinois hit finder hit its 200-iteration limit (surface.py:403) */
 #define OTB_STATUS_NBELOW1 2       /* refraction index < 1 (refraction_index.py:165) */
 #define OTB_STATUS_UNSUPPORTED 4
+#define OTB_STATUS_Z_DECREASE 16   /* informational: some stored z decreased from one section to the next */
 #define OTB_STATUS_NEG_DIR 8       /* generated direction with s_z <= 0 (ray_source.py:353) */
 
 /* Selects the CUDA device for the calling thread and verifies it is sm_100 (no CPU fallback). */

@@ -57,7 +57,7 @@ class OtbRays(C.Structure):
 class OtbRayStore(C.Structure):
     _fields_ = [("N", C.c_int64), ("nt", C.c_int32), ("pad", C.c_int32), ("p_d", C.c_void_p),
                 ("s_d", C.c_void_p), ("pol_d", C.c_void_p), ("w_d", C.c_void_p), ("n_d", C.c_void_p),
-                ("wl_d", C.c_void_p)]
+                ("wl_d", C.c_void_p), ("trace_status_d", C.c_void_p)]
 
 
 class OtbDetector(C.Structure):

@@ -43,7 +43,9 @@ struct DetArgs {
     int* status;
 };
 
-__global__ void __launch_bounds__(128) detector_hits_kernel(const DetArgs a)
+#define OTB_DET_COARSE 8      // coarse samples of the two-level section search: covers nt <= 32
+
+__global__ void __launch_bounds__(128, 6) detector_hits_kernel(const DetArgs a)
 {
     const int64_t N = a.st.N;
     const int nt = a.st.nt;
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(128) detector_hits_kernel(const DetArgs a)
     const KSurface& S = a.surf;
     const int64_t ray = a.begin + (int64_t)blockIdx.x*blockDim.x + threadIdx.x;
     const bool valid = ray < a.end;
+    const bool monotone = a.st.trace_status_d && !(__ldg(a.st.trace_status_d) & OTB_STATUS_Z_DECREASE);
 
     float w = 0.0f;
     double X = 0.0, Y = 0.0;
@@ -61,27 +64,54 @@ __global__ void __launch_bounds__(128) detector_hits_kernel(const DetArgs a)
         // section straddling the detector z-extent (raytracer.py:929-938)
         bool no_start = true, no_reach = true;
         int first_ge = -1;
-        // the z plane of every section is read once; four independent loads in flight per thread
         const double* __restrict__ Pz = P + ray + 2*Nnt;
-        int j = 0;
-        for (; j + 4 <= nt; j += 4) {
-            double z[4];
+        if (monotone && nt <= 4*OTB_DET_COARSE) {
+            // z never decreases along a ray (reported by the trace): two batches of independent loads instead of
+            // a scan over all nt sections or a bisection of dependent loads (the kernel is bound by the number
+            // of DRAM round trips per ray, not by bytes): every 4th section plus the last one, then the three
+            // sections inside the bracket that contains the first z >= z_min
+            double zc[OTB_DET_COARSE + 1];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) z[u] = __ldcs(Pz + N*(int64_t)(j + u));
+            for (int u = 0; u < OTB_DET_COARSE; ++u) zc[u] = (4*u < nt) ? __ldcs(Pz + N*(int64_t)(4*u)) : INFINITY;
+            const double zl = __ldcs(Pz + N*(int64_t)(nt - 1));
+            const double z0 = zc[0];
+            no_start = (z0 >= S.z_min) && (z0 >= S.z_max);
+            no_reach = !(zl >= S.z_min) && !(zl >= S.z_max);
+            if (z0 >= S.z_min) first_ge = 0;
+            else if (zl >= S.z_min) {
+                int kb = 0;                            // last coarse sample below z_min
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const bool bmin = z[u] >= S.z_min, bmax = z[u] >= S.z_max;
+                for (int u = 1; u < OTB_DET_COARSE; ++u) if (4*u < nt && !(zc[u] >= S.z_min)) kb = u;
+                const int j0 = 4*kb;                   // z[j0] < z_min, first_ge in (j0, min(j0 + 4, nt - 1)]
+                double zf[3];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) zf[u] = (j0 + 1 + u < nt) ? __ldcs(Pz + N*(int64_t)(j0 + 1 + u)) : INFINITY;
+                first_ge = (j0 + 4 < nt - 1) ? j0 + 4 : nt - 1;
+#pragma unroll
+                for (int u = 2; u >= 0; --u) if (j0 + 1 + u < nt && zf[u] >= S.z_min) first_ge = j0 + 1 + u;
+            }
+        } else {
+            // the z plane of every section is read once; four independent loads in flight per thread
+            int j = 0;
+            for (; j + 4 <= nt; j += 4) {
+                double z[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) z[u] = __ldcs(Pz + N*(int64_t)(j + u));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool bmin = z[u] >= S.z_min, bmax = z[u] >= S.z_max;
+                    no_start = no_start && (bmin && bmax);
+                    no_reach = no_reach && (!bmin && !bmax);
+                    if (first_ge < 0 && bmin) first_ge = j + u;
+                }
+            }
+            for (; j < nt; ++j) {
+                const double z = __ldcs(Pz + N*(int64_t)j);
+                const bool bmin = z >= S.z_min, bmax = z >= S.z_max;
                 no_start = no_start && (bmin && bmax);
                 no_reach = no_reach && (!bmin && !bmax);
-                if (first_ge < 0 && bmin) first_ge = j + u;
+                if (first_ge < 0 && bmin) first_ge = j;
             }
-        }
-        for (; j < nt; ++j) {
-            const double z = __ldcs(Pz + N*(int64_t)j);
-            const bool bmin = z >= S.z_min, bmax = z >= S.z_max;
-            no_start = no_start && (bmin && bmax);
-            no_reach = no_reach && (!bmin && !bmax);
-            if (first_ge < 0 && bmin) first_ge = j;
         }
         if (!(no_start || no_reach)) {
             int sec = (first_ge < 0 ? 0 : first_ge) - 1;

@@ -25,6 +25,7 @@ struct StoreCursor {
     float* pw;
     double* pn;
     float* ppol;
+    bool z_decrease;   // some section of this ray ended at a smaller z than it started
 };
 
 // one sequential step: trace, book messages, store section i+1
@@ -47,7 +48,9 @@ __device__ __forceinline__ void store_step(const KScene& sc, const TraceArgs& a,
         }
     }
     StepFlags fl;
+    const double z_prev = r.p.z;
     trace_step<POL, CAPS>(sc, a.sc.aux, st, r, fl, za, zb, a.status);
+    c.z_decrease = c.z_decrease | (r.p.z < z_prev);
     book_step(smsgs, nt, i, valid, fl);
 
     c.pp += N;
@@ -109,6 +112,7 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
 
         // running plane pointers: one add per plane and section instead of 64-bit index arithmetic
         StoreCursor cur;
+        cur.z_decrease = false;
         cur.pp = a.out.p_d + rr;
         cur.pw = a.out.w_d + rr;
         cur.pn = a.out.n_d + rr;
@@ -140,6 +144,7 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
 #else
         for (int i = 0; i < sc.n_steps; ++i) store_step<POL, CAPS>(sc, a, i, r, cur, smsgs, valid, rr);
 #endif
+        if (valid && cur.z_decrease) atomicOr(a.status, OTB_STATUS_Z_DECREASE);    // practically never
         if (valid) {
             __stcs(&a.out.s_d[rr], r.s.x);
             __stcs(&a.out.s_d[rr + N], r.s.y);

@@ -192,12 +192,14 @@ class DeviceStore:
         self.n = torch.empty(N*nt, dtype=torch.float64, device=d)
         self.wl = torch.empty(N, dtype=torch.float32, device=d)
         self.pol = None if no_pol else torch.empty(N*nt*3, dtype=torch.float32, device=d)
+        self.status = None      # status tensor of the trace that filled the store
 
     def c_struct(self):
         s = _cabi.OtbRayStore()
         s.N, s.nt = self.N, self.nt
         s.p_d, s.s_d, s.pol_d = dptr(self.p), dptr(self.s), dptr(self.pol)
         s.w_d, s.n_d, s.wl_d = dptr(self.w), dptr(self.n), dptr(self.wl)
+        s.trace_status_d = dptr(self.status)
         return s
 
     @staticmethod
@@ -224,6 +226,7 @@ def trace_store(scene: SceneHandle, rays: DeviceRays, store: DeviceStore | None 
     if events is not None:
         events[1].record()
     check(rc, scene.lib)
+    store.status = status        # the detector search reads OTB_STATUS_Z_DECREASE from it on the device
     if sync:
         raise_status(int(status.item()))
     return store, msgs.view(_cabi.NMSG, scene.nt), status

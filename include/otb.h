@@ -315,6 +315,26 @@ int otb_scene_destroy(OtbScene* scene);
  * re-upload the scene at every trace (the reference re-walks its object tree per trace, raytracer.py:297-305). */
 int otb_scene_update(OtbScene* scene, const OtbSceneDesc* desc, void* stream);
 
+/* ---- image post-processing: RenderImage.get (render_image.py:131-222) -------------------------------------
+ * Join-bins rescaling and per-pixel conversion of the (Ny, Nx, 4) XYZW histogram on the device; replaces
+ * cv2.resize(INTER_AREA) + color.xyz_to_srgb / xyz_to_luv / luv_hue / luv_chroma / luv_saturation /
+ * outside_srgb_gamut (color/srgb.py:118-407, color/luv.py:20-139) of the reference's host path. */
+typedef enum OtbImageMode {
+    OTB_IMG_IRRADIANCE = 0, OTB_IMG_ILLUMINANCE = 1, OTB_IMG_SRGB_ABSOLUTE = 2, OTB_IMG_SRGB_PERCEPTUAL = 3,
+    OTB_IMG_OUTSIDE_GAMUT = 4, OTB_IMG_LIGHTNESS = 5, OTB_IMG_HUE = 6, OTB_IMG_CHROMA = 7, OTB_IMG_SATURATION = 8
+} OtbImageMode;
+#define OTB_IMG_NSTATS 8
+/* out (Ny/fact, Nx/fact, 4) = block means of img (Ny, Nx, 4); fact must divide both sides (render_image.py:164-174) */
+int otb_image_rescale(const double* img_d, int32_t Ny, int32_t Nx, int32_t fact, double* out_d, void* stream);
+/* image-wide extrema the conversions normalise by, into stats_d[OTB_IMG_NSTATS] (layout: otb_image.cu).
+ * pass 1: everything that depends on the pixels only; pass 2 (param = L_th) and pass 3 (param = chroma_scale):
+ * the two statistics of the perceptual rendering intent that depend on earlier ones (srgb.py:238-262, 331-354) */
+int otb_image_stats(const double* img_d, int64_t npx, int32_t pass, double param, double* stats_d, void* stream);
+/* out (npx) or (npx, 3) for the two sRGB modes.  scale: 1/Apx (irradiance) or K/Apx (illuminance);
+ * chroma_scale: perceptual intent only, negative = no colour outside the gamut (plain conversion, srgb.py:308-310) */
+int otb_image_convert(const double* img_d, int64_t npx, int32_t mode, double scale, double chroma_scale,
+                      const double* stats_d, double* out_d, void* stream);
+
 /* Store-mode trace: replaces Raytracer.trace's sub_trace surface loop (raytracer.py:297-397)
  * including find_hit, __refraction, __compute_polarization, __refraction_ideal_lens, __hurb,
  * __outline_intersection, Filter/Aperture handling.  msgs_d: int64[OTB_NMSG * nt], accumulated. */

@@ -435,3 +435,37 @@ def sphere_projection(surf, p: np.ndarray, method: str) -> np.ndarray:
     out = torch.empty(3*max(N, 1), dtype=torch.float64, device=device())
     check(lib.otb_sphere_projection(C.byref(det.surface), rec["projection"], N, dptr(pd), dptr(out), stream_ptr()), lib)
     return out[:3*N].cpu().numpy().reshape((N, 3), order="F")
+
+
+# ---------------------------------------------------------------------------------------------------
+# image post-processing (RenderImage.get, render_image.py:131-222)
+# ---------------------------------------------------------------------------------------------------
+def image_get(data_dev, fact: int, mode: int, scale: float, L_th: float, chroma_scale):
+    """join-bins rescale + conversion of a device (Ny, Nx, 4) histogram; returns the host array of the result"""
+    torch = _torch()
+    lib = ensure_init()
+    Ny, Nx, _ = data_dev.shape
+    st = stream_ptr()
+    if fact != 1:
+        img = torch.empty((Ny//fact, Nx//fact, 4), dtype=torch.float64, device=data_dev.device)
+        check(lib.otb_image_rescale(dptr(data_dev), Ny, Nx, fact, dptr(img), st), lib)
+    else:
+        img = data_dev
+    H, W = int(img.shape[0]), int(img.shape[1])
+    npx = H*W
+    stats = torch.empty(8, dtype=torch.float64, device=data_dev.device)
+    cs = -1.0
+    if mode >= 2:           # every mode but irradiance / illuminance normalises by image-wide extrema
+        check(lib.otb_image_stats(dptr(img), npx, 1, 0.0, dptr(stats), st), lib)
+    if mode == 3:           # perceptual intent: srgb.py:303-352
+        s1 = stats.cpu().numpy()
+        if s1[1] != 0.0 or chroma_scale is not None:
+            check(lib.otb_image_stats(dptr(img), npx, 2, L_th, dptr(stats), st), lib)
+            cmin = float(stats[6].item())
+            cr = np.sqrt(cmin) if np.isfinite(cmin) else 1.0
+            fact_c = float(np.clip(cr, 0.32, 1.0))
+            cs = float(chroma_scale) if chroma_scale is not None else fact_c
+            check(lib.otb_image_stats(dptr(img), npx, 3, cs, dptr(stats), st), lib)
+    out = torch.empty((H, W, 3) if mode in (2, 3) else (H, W), dtype=torch.float64, device=data_dev.device)
+    check(lib.otb_image_convert(dptr(img), npx, mode, float(scale), cs, dptr(stats), dptr(out), st), lib)
+    return out.cpu().numpy()

@@ -87,6 +87,21 @@ class RGBImage(_BaseImage):
         return d
 
 
+class ScalarImage(_BaseImage):
+    """image/scalar_image.py: one channel, non-negative values (irradiance, illuminance, CIELUV channels ...)"""
+    _channels = 1
+
+    def _check_data(self, d):
+        if d.ndim == 3:
+            raise ValueError("Image can't have color information. Either use a RGBImage or remove color information.")
+        if d.ndim != 2:
+            raise ValueError(f"Image needs to have two dimensions but has shape {d.shape}.")
+        if d.size and (m := d.min()) < 0.0:
+            raise ValueError(f"There is a negative value of {m} inside the image. Make sure all image data is "
+                             "non-negative.")
+        return d
+
+
 class GrayscaleImage(_BaseImage):
     """image/grayscale_image.py"""
     _channels = 1
@@ -110,6 +125,11 @@ class RenderImage:
     SIZES = [1, 3, 5, 7, 9, 15, 21, 27, 35, 45, 63, 105, 135, 189, 315, 945]
     MAX_IMAGE_SIDE = SIZES[-1]
     MAX_IMAGE_RATIO = SIZES[2]
+    image_modes = ["sRGB (Absolute RI)", "sRGB (Perceptual RI)", "Outside sRGB Gamut", "Irradiance", "Illuminance",
+                   "Lightness (CIELUV)", "Hue (CIELUV)", "Chroma (CIELUV)", "Saturation (CIELUV)"]
+    _MODE_IDS = {"Irradiance": 0, "Illuminance": 1, "sRGB (Absolute RI)": 2, "sRGB (Perceptual RI)": 3,
+                 "Outside sRGB Gamut": 4, "Lightness (CIELUV)": 5, "Hue (CIELUV)": 6, "Chroma (CIELUV)": 7,
+                 "Saturation (CIELUV)": 8}
 
     def __init__(self, extent, projection: str = None, desc: str = "", long_desc: str = ""):
         e = np.array(np.asarray_chkfinite(extent, dtype=np.float64))
@@ -248,6 +268,31 @@ class RenderImage:
             self._wait_device()
             return float(self.K*self._data_dev[:, :, 1].sum().item())
         return float(self.K*np.sum(self._materialise()[:, :, 1]))
+
+    def get(self, mode: str, N: int = 315, L_th: float = 0, chroma_scale: float = None):
+        """RenderImage.get (render_image.py:131-222): converted image of mode `mode`, rescaled by joining bins to
+        N pixels on the smaller side (nearest of SIZES).  Rescaling and all per-pixel conversions run on the
+        device (engine.image_get -> otb_image_rescale / otb_image_stats / otb_image_convert); the result is an
+        RGBImage (sRGB modes) or a ScalarImage like in the reference."""
+        from . import engine
+        if not self.has_image():
+            raise RuntimeError("Image was not calculated/rendered yet.")
+        N = int(N)
+        if not 1 <= N <= self.MAX_IMAGE_SIDE:
+            raise ValueError(f"N needs to be between 1 and {self.MAX_IMAGE_SIDE}")
+        if mode not in self._MODE_IDS:
+            raise ValueError(f"Invalid display_mode {mode}, should be one of {self.image_modes}.")
+        iargs = dict(extent=self.extent, projection=self.projection, desc=self.desc, long_desc=self.long_desc,
+                     quantity=mode, limit=self.limit)
+        Na = self.SIZES[int(np.argmin(np.abs(N - np.array(self.SIZES))))]
+        fact = int(self.MAX_IMAGE_SIDE/Na)
+        if self._data_dev is None:                       # image rendered elsewhere and assigned from the host
+            import torch
+            self._data_dev = torch.from_numpy(np.ascontiguousarray(self._data)).to(engine.device())
+        self._wait_device()
+        scale = {"Irradiance": 1/self.Apx, "Illuminance": self.K/self.Apx}.get(mode, 0.0)
+        data = engine.image_get(self._data_dev, fact, self._MODE_IDS[mode], scale, float(L_th), chroma_scale)
+        return RGBImage(data, **iargs) if data.ndim == 3 else ScalarImage(data, **iargs)
 
     def render(self, p: np.ndarray = None, w: np.ndarray = None, wl: np.ndarray = None,
                limit: float = None, _dont_filter: bool = False) -> None:

@@ -68,27 +68,28 @@ __device__ __forceinline__ void strat_ring(const GenCtx& g, uint32_t stream, dou
     double x, y;
     strat2(g, stream, -r, r, -r, r, x, y);
     double x2 = x*x, y2 = y*y, r_ = 0.0, theta = 0.0;
-    if (x2 > y2) {
+    if (x2 > y2) {             // theta in units of pi
         r_ = x;
-        theta = 0.7853981633974483*y/x;
+        theta = 0.25*y/x;
     } else if (y2 > 0) {
         r_ = y;
-        theta = 1.5707963267948966 - 0.7853981633974483*x/y;
+        theta = 0.5 - 0.25*x/y;
     }
     if (ri != 0.0) {
         double q = ri/r;
         double v = sqrt(ri*ri + r_*r_*(1 - q*q));
         r_ = (r_ < 0) ? -v : v;
     }
+    // theta is a rational multiple of pi by construction: sincospi needs no argument reduction
     if (!polar) {
         double sn, cs;
-        sincos(theta, &sn, &cs);
+        sincospi(theta, &sn, &cs);
         o1 = r_*cs;
         o2 = r_*sn;
     } else {
-        if (r_ < 0) theta -= 3.141592653589793;
+        if (r_ < 0) theta -= 1.0;
         o1 = fabs(r_);
-        o2 = theta;
+        o2 = theta;            // in units of pi
     }
 }
 
@@ -258,7 +259,7 @@ generate_kernel(const __grid_constant__ GenArgs a)
             // (asin / acos of the sampled radius) they are computed algebraically instead of through
             // inverse + forward trigonometry; alpha goes through one sincos
             double theta = 0.0, alpha, ct = 0.0, stt = 0.0;
-            bool have_sc = false;
+            bool have_sc = false, alpha_pi = false;       // alpha_pi: alpha is given in units of pi
             if (S.div_2d) {
                 Philox4 r = draw(g, ST_DIV2);
                 // two equally likely half-planes; stratified over the rays like the reference's discrete draw
@@ -274,6 +275,7 @@ generate_kernel(const __grid_constant__ GenArgs a)
             } else {
                 double rr;
                 strat_ring(g, ST_DIV, 0.0, S.div_sin, true, rr, alpha);
+                alpha_pi = true;
                 if (S.divergence == OTB_DIV_LAMBERTIAN) {            // theta = asin(r)
                     stt = rr;
                     ct = sqrt(1 - rr*rr);
@@ -294,7 +296,7 @@ generate_kernel(const __grid_constant__ GenArgs a)
             V3 sx = cross3(so, sy);
             double ca, sa;
             if (!have_sc) sincos(theta, &stt, &ct);
-            sincos(alpha, &sa, &ca);
+            if (alpha_pi) sincospi(alpha, &sa, &ca); else sincos(alpha, &sa, &ca);
             s = v3(ct*so.x + stt*(ca*sx.x + sa*sy.x), ct*so.y + stt*(ca*sx.y + sa*sy.y), ct*so.z + stt*(ca*sx.z + sa*sy.z));
         }
         if (!(s.z > 0)) atomicOr(status, OTB_STATUS_NEG_DIR);
@@ -302,9 +304,10 @@ generate_kernel(const __grid_constant__ GenArgs a)
         // ---- polarisation (ray_source.py:359-433)
         if (!no_pol) {
             double ang;
+            bool ang_pi = false;                           // angle given in units of pi
             switch (S.polarization) {
             case OTB_POL_CONSTANT: ang = S.pol_angle; break;
-            case OTB_POL_UNIFORM: ang = strat1(g, ST_POL, 0.0, 6.283185307179586); break;
+            case OTB_POL_UNIFORM: ang = strat1(g, ST_POL, 0.0, 2.0); ang_pi = true; break;
             case OTB_POL_LIST: {
                 const double* x = aux + S.pol_tab_off;
                 const double* F = x + S.pol_tab_n;
@@ -320,7 +323,7 @@ generate_kernel(const __grid_constant__ GenArgs a)
             }
             }
             double sang, cang;
-            sincos(ang, &sang, &cang);
+            if (ang_pi) sincospi(ang, &sang, &cang); else sincos(ang, &sang, &cang);
             V3 pol = v3(cang, sang, 0.0);
             if (s.z != 1) {
                 double fa = 1/(sqrt(1 - s.z*s.z) + 1e-16);

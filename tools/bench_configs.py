@@ -39,13 +39,14 @@ def gpu_time(f, n=5, w=2):
 
 
 rows = []
-for name, mode in (("spherical_aberration", "store"), ("double_gauss", "store"), ("arizona_eye", "store"),
-                   ("image_render", "fused6"), ("cosine_surfaces", "store"), ("hurb_square", "store"),
-                   ("hurb_pinhole", "store"), ("zoo_analytic", "store"), ("zoo_numeric", "store")):
+CASES = [(n, m, False) for n, m in (("spherical_aberration", "store"), ("double_gauss", "store"), ("arizona_eye", "store"),
+                                    ("image_render", "fused6"), ("cosine_surfaces", "store"), ("hurb_square", "store"),
+                                    ("hurb_pinhole", "store"), ("zoo_analytic", "store"), ("zoo_numeric", "store"))]
+CASES += [(n, m, True) for n, m in (("double_gauss", "store"), ("arizona_eye", "store"), ("image_render", "fused6"))]
+for name, mode, want_spec in CASES:
     RT = scenes.SCENES[name](ot)
-    spec = False
-    if name in ("double_gauss", "arizona_eye", "image_render", "zoo_analytic"):
-        spec = RT.compile()
+    RT.use_specialised_kernels = want_spec
+    spec = RT.compile() if want_spec else False
     N = args.rays
     nt = len(RT.tracing_surfaces) + 2
     if mode == "store":

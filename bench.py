@@ -325,6 +325,20 @@ def run_gpu(args):
         peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
         n_local = args.rays
         alg_bytes = n_local*(nt*48 + 28) + n_local*68
+        # DRAM traffic of the trace kernel from the committed `ncu --set full` capture of this same workload
+        # (profiles/, dram__bytes_read.sum + dram__bytes_write.sum per launch); only valid for the default size
+        traffic = None
+        prof = ROOT / "profiles" / "r1_trace_store_final_ncu.csv"
+        if prof.exists() and args.rays == RAYS_PER_GPU:
+            try:
+                tb = 0.0
+                for ln in prof.read_text().splitlines():
+                    c = ln.split(",")
+                    if c[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                        tb += float(c[2])*{"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[c[1]]
+                traffic = tb or None
+            except Exception:
+                traffic = None
         achieved = alg_bytes/(kernel_ms*1e-3)/1e9
         units = N_total*(nt - 1)
         line = {
@@ -342,19 +356,22 @@ def run_gpu(args):
                        ("generic_trace_kernel_ms" if specialised else "specialised_trace_kernel_ms"): other_ms, "trace_only_ray_surfaces_per_s": n_local*world*(nt - 1)/(kernel_ms*1e-3),
                        "image_power_W": power},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved/peak_gbs,
-                         "traffic": None, "kernel": "trace_store_kernel<POL>", "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": "profiles/r1_trace_store_final_ncu.csv (ncu --set full, same workload)",
+                         "kernel": "trace_store_kernel<POL, LENS>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "e2e": {"value": units/(e2e_ms*1e-3), "unit": "ray*surface/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out.nbytes),
                     "pipelining": "image download of step k overlaps the trace of step k+1 (depth 1)"},
-            "gpu_launches": 4*args.steps,
+            "gpu_launches": 8*args.steps,     # generate, trace_store, detector_hits, render x (resident + e2e region)
             "clocks": clk,
         }
         if not args.no_cpu and world == 1:
-            v, dt, used, _ = run_cpu(args, 1, 1, CPU_SAMPLE_RAYS)
+            CPU_STEPS = 24      # ~10 s of host work: 24 bundles of CPU_SAMPLE_RAYS rays through the same scene
+            v, dt, used, _ = run_cpu(args, CPU_STEPS, 1, CPU_SAMPLE_RAYS)
             line["cpu_baseline"] = {"value": v, "unit": "ray*surface/s", "cores": used, "kind": "port",
-                                    "sample": f"{CPU_SAMPLE_RAYS} rays of the same scene, trace + detector image, "
-                                              f"{dt:.1f} s; numpy oracle port, reference thread scheme",
+                                    "sample": f"{CPU_STEPS} x {CPU_SAMPLE_RAYS} rays of the same scene, trace + detector "
+                                              f"image, {dt*CPU_STEPS:.1f} s in total; numpy oracle port, reference "
+                                              f"thread scheme",
                                     "ms_per_surface_per_Mray": 1e9/v}
         print(json.dumps(line))
     if world > 1:

@@ -20,6 +20,12 @@ struct TraceArgs {
     int* status;
 };
 
+#ifndef OTB_STEP_UNROLL
+#define OTB_STEP_UNROLL 1
+#endif
+#define OTB_STR(x) #x
+#define OTB_UNROLL_N(n) _Pragma(OTB_STR(unroll n))
+
 struct StoreCursor {
     double* pp;     // p plane x of the current section (y, z at +N*nt, +2*N*nt)
     float* pw;
@@ -142,6 +148,7 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
 #define OTB_CALL_STORE_STEP(i) store_step<POL, CAPS>(sc, a, i, r, cur, smsgs, valid, rr);
         OTB_SPEC_FOREACH_STEP(OTB_CALL_STORE_STEP)
 #else
+        OTB_UNROLL_N(OTB_STEP_UNROLL)
         for (int i = 0; i < sc.n_steps; ++i) store_step<POL, CAPS>(sc, a, i, r, cur, smsgs, valid, rr);
 #endif
         if (valid && cur.z_decrease) atomicOr(a.status, OTB_STATUS_Z_DECREASE);    // practically never

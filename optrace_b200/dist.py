@@ -58,6 +58,9 @@ def allreduce_sum_(t):
     return t
 
 
+_image_group = None
+
+
 def allreduce_sum_async(tensors):
     """SUM all-reduce of GPU tensors on the side stream, ordered after the work queued so far on the current
     stream.  Returns the CUDA event that marks completion (None when there is nothing to reduce): the caller's
@@ -67,11 +70,16 @@ def allreduce_sum_async(tensors):
     import torch
     from . import engine
     td = _td()
+    global _image_group
+    if _image_group is None:
+        # own communicator (own NCCL stream): the small synchronous collectives of the next trace (per-source ray
+        # counts, messages) must not queue behind a 143 MB image all-reduce.  Created collectively at first use.
+        _image_group = td.new_group(backend=td.get_backend())
     side = engine.side_stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for t in tensors:
-            td.all_reduce(t, op=td.ReduceOp.SUM)
+            td.all_reduce(t, op=td.ReduceOp.SUM, group=_image_group)
             t.record_stream(side)
         ev = torch.cuda.Event()
         ev.record(side)

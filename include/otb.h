@@ -84,6 +84,9 @@ typedef enum OtbSurfKind {
 #define OTB_P_KRHO2 7      /* k*rho**2 */
 #define OTB_P_EDGEZ 8      /* _values(r - N_EPS, 0): radially continued edge value (surface.py:162) */
 #define OTB_P_FDEPS 9      /* finite-difference step of Surface.normals (surface.py:266-270) */
+#define OTB_P_ZMIN_E 11    /* CONIC: z_min - N_EPS (conic_surface.py:160) */
+#define OTB_P_ZMAX_E 12    /* CONIC: z_max + N_EPS */
+#define OTB_P_RB2 13       /* CONIC: (r + N_EPS)^2 (Surface.mask, surface.py:235-245) */
 /* TILTED */
 #define OTB_P_NX 0
 #define OTB_P_NY 1

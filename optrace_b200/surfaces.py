@@ -434,6 +434,10 @@ class ConicSurface(Surface):
         p[6], p[7] = (k+1)*rho**2, k*rho**2
         p[8] = self._edge_z()
         p[9] = self._fd_eps()
+        # warp-uniform values of the hit test (conic_surface.py:160-161, surface.py:235-245) with the reference's own
+        # float64 expressions: z_min - N_EPS, z_max + N_EPS, (r + N_EPS)^2
+        rb = float(self.r) + self.N_EPS
+        p[11], p[12], p[13] = float(self.z_min) - self.N_EPS, float(self.z_max) + self.N_EPS, rb*rb
 
     def _record(self):
         rec = self._base_record()

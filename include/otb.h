@@ -318,6 +318,11 @@ int otb_scene_destroy(OtbScene* scene);
  * re-upload the scene at every trace (the reference re-walks its object tree per trace, raytracer.py:297-305). */
 int otb_scene_update(OtbScene* scene, const OtbSceneDesc* desc, void* stream);
 
+/* Resolution-limit filter, RenderImage._apply_rayleigh_filter (render_image.py:255-296): out = max(img (*) psf, 0),
+ * zero padded "same" convolution of every XYZW channel with the host-built (K, K) Airy-disc table, K odd.
+ * Replaces scipy.signal.fftconvolve of the reference's host path (direct convolution: the kernel is compact). */
+int otb_image_convolve(const double* img_d, int32_t Ny, int32_t Nx, const double* psf_d, int32_t K, double* out_d, void* stream);
+
 /* ---- image post-processing: RenderImage.get (render_image.py:131-222) -------------------------------------
  * Join-bins rescaling and per-pixel conversion of the (Ny, Nx, 4) XYZW histogram on the device; replaces
  * cv2.resize(INTER_AREA) + color.xyz_to_srgb / xyz_to_luv / luv_hue / luv_chroma / luv_saturation /

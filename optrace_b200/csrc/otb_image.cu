@@ -357,6 +357,42 @@ __global__ void __launch_bounds__(256) image_rescale_kernel(const double* __rest
     }
 }
 
+// Resolution-limit filter (RenderImage._apply_rayleigh_filter, render_image.py:255-296): the XYZW histogram is
+// convolved with the Airy-disc kernel the host built (scipy.special.j1, a (2 ps + 1)^2 table), zero padded
+// ("same"), negatives removed.  The reference goes through an FFT; the kernel has compact support (third zero of
+// the Airy pattern), so this is a direct convolution: thread = pixel (4 channels = two 128-bit loads per tap),
+// taps outside the support are skipped warp-uniformly, the PSF table is read through the read-only cache.
+__global__ void __launch_bounds__(256) image_convolve_kernel(const double* __restrict__ img, int Ny, int Nx,
+                                                             const double* __restrict__ psf, int K, double* __restrict__ out)
+{
+    const int x = blockIdx.x*32 + (threadIdx.x & 31), y = blockIdx.y*8 + (threadIdx.x >> 5);
+    if (x >= Nx || y >= Ny) return;
+    const int ps = K >> 1;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int j = 0; j < K; ++j) {
+        const int yy = y + ps - j;                  // out[y] = sum_j in[y + ps - j] * psf[j]  (true convolution)
+        if (yy < 0 || yy >= Ny) continue;
+        const double* __restrict__ prow = psf + (int64_t)j*K;
+        const double2* __restrict__ irow = (const double2*)(img + (int64_t)yy*Nx*4);
+        for (int i = 0; i < K; ++i) {
+            const double pv = __ldg(prow + i);
+            if (pv == 0.0) continue;
+            const int xx = x + ps - i;
+            if (xx < 0 || xx >= Nx) continue;
+            const double2 v01 = __ldg(irow + 2*xx), v23 = __ldg(irow + 2*xx + 1);
+            a0 += v01.x*pv;
+            a1 += v01.y*pv;
+            a2 += v23.x*pv;
+            a3 += v23.y*pv;
+        }
+    }
+    double* o = out + ((int64_t)y*Nx + x)*4;        // "remove negative values that can arise by fft": none arise here
+    o[0] = a0 < 0 ? 0.0 : a0;
+    o[1] = a1 < 0 ? 0.0 : a1;
+    o[2] = a2 < 0 ? 0.0 : a2;
+    o[3] = a3 < 0 ? 0.0 : a3;
+}
+
 int otb_sm_count();
 
 extern "C" {
@@ -403,6 +439,16 @@ int otb_image_convert(const double* img_d, int64_t npx, int32_t mode, double sca
     a.img = img_d; a.out = out_d; a.stats = stats_d; a.npx = npx; a.mode = mode; a.scale = scale; a.chroma_scale = chroma_scale;
     const int blocks = (int)((npx + 255)/256 < 8LL*otb_sm_count() ? (npx + 255)/256 : 8LL*otb_sm_count());
     image_convert_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    OTB_CUDA(cudaGetLastError());
+    return OTB_OK;
+}
+
+int otb_image_convolve(const double* img_d, int32_t Ny, int32_t Nx, const double* psf_d, int32_t K, double* out_d, void* stream)
+{
+    if (!img_d || !psf_d || !out_d || img_d == out_d) { otb_set_error("invalid argument"); return OTB_ERR_INVALID_ARG; }
+    if (Ny < 1 || Nx < 1 || K < 1 || !(K & 1)) { otb_set_error("the filter kernel needs an odd side length"); return OTB_ERR_INVALID_ARG; }
+    dim3 grid((Nx + 31)/32, (Ny + 7)/8);
+    image_convolve_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img_d, Ny, Nx, psf_d, K, out_d);
     OTB_CUDA(cudaGetLastError());
     return OTB_OK;
 }

@@ -469,3 +469,15 @@ def image_get(data_dev, fact: int, mode: int, scale: float, L_th: float, chroma_
     out = torch.empty((H, W, 3) if mode in (2, 3) else (H, W), dtype=torch.float64, device=data_dev.device)
     check(lib.otb_image_convert(dptr(img), npx, mode, float(scale), cs, dptr(stats), dptr(out), st), lib)
     return out.cpu().numpy()
+
+
+def image_convolve(data_dev, psf: np.ndarray):
+    """otb_image_convolve: zero-padded "same" convolution of every channel of a device (Ny, Nx, 4) image with a
+    host (K, K) kernel, negatives removed; returns a new device tensor"""
+    torch = _torch()
+    lib = ensure_init()
+    Ny, Nx, _ = data_dev.shape
+    psf_d = torch.from_numpy(np.ascontiguousarray(psf, dtype=np.float64)).to(data_dev.device)
+    out = torch.empty_like(data_dev)
+    check(lib.otb_image_convolve(dptr(data_dev), Ny, Nx, dptr(psf_d), int(psf.shape[0]), dptr(out), stream_ptr()), lib)
+    return out

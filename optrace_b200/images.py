@@ -296,13 +296,45 @@ class RenderImage:
 
     def render(self, p: np.ndarray = None, w: np.ndarray = None, wl: np.ndarray = None,
                limit: float = None, _dont_filter: bool = False) -> None:
-        """render_image.py:361-421 with the scatter-add done by the CUDA engine."""
+        """render_image.py:361-421 with the scatter-add (and the resolution filter) done by the CUDA engine."""
         from . import engine
-        if limit is not None:
-            raise NotImplementedError("The Rayleigh/Airy `limit` filter is post-processing outside the "
-                                      "accelerated path (SURVEY.md §8f rank 2).")
         self._limit = limit
         self._fix_extent()
         Nx, Ny = self._grid()
         self._data = None
         self._data_dev, self._counts_dev = engine.render_xyzw_host(p, w, wl, self.extent, Nx, Ny)
+        if not _dont_filter and self._limit is not None:
+            self._apply_rayleigh_filter()
+
+    def _airy_psf(self) -> np.ndarray:
+        """Airy-disc kernel of the resolution filter, render_image.py:261-280 verbatim in numpy/scipy: host setup of
+        a (2 ps + 1)^2 table, not per-ray work"""
+        import scipy.special
+        Ny, Nx = self.shape[:2]
+        px = self._limit/1000.0/(self.s[0]/Nx)
+        py = self._limit/1000.0/(self.s[1]/Ny)
+        ps = int(np.ceil(2.7*max(px, py)))
+        ps = ps + 1 if ps % 2 else ps
+        Y, X = np.mgrid[-ps:ps:(2*ps + 1)*1j, -ps:ps:(2*ps + 1)*1j]
+        R = np.sqrt((X/px)**2 + (Y/py)**2)*3.8317
+        Rnz = R[R != 0]
+        psf = np.ones((2*ps + 1, 2*ps + 1), dtype=np.float64)
+        psf[R != 0] = (2*scipy.special.j1(Rnz)/Rnz)**2
+        psf[R > 10.1735] = 0
+        psf *= 1/psf.sum()
+        return psf
+
+    def _apply_rayleigh_filter(self) -> None:
+        """RenderImage._apply_rayleigh_filter (render_image.py:255-296): convolution of the XYZW histogram with the
+        Airy-disc kernel on the device (otb_image_convolve)"""
+        from . import engine
+        if self._limit is not None and self.projection is not None:
+            raise RuntimeError("Resolution limit filter is not applicable for a projected image.")
+        if not self.has_image():
+            raise RuntimeError("Image was not calculated/rendered yet.")
+        if self._data_dev is None:
+            import torch
+            self._data_dev = torch.from_numpy(np.ascontiguousarray(self._data)).to(engine.device())
+        self._wait_device()
+        self._data_dev = engine.image_convolve(self._data_dev, self._airy_psf())
+        self._data = None

@@ -396,9 +396,11 @@ class Raytracer(Group):
     def detector_image(self, detector_index: int = 0, source_index: int = None, extent=None, limit: float = None,
                        projection_method: str = "Equidistant", **kwargs) -> RenderImage:
         """Raytracer.detector_image (raytracer.py:1053-1098)"""
-        if limit is not None:
-            raise NotImplementedError("The Rayleigh/Airy `limit` filter is post-processing outside the accelerated "
-                                      "path (SURVEY.md §8f rank 2).")
+        dont_filter = bool(kwargs.get("_dont_filter", False))
+        if limit is not None and extent is not None and not dont_filter:
+            warning("Using the limit parameter in combination with a user defined extent"
+                    " will produce an incorrect detector image, as the rays outside the extent"
+                    " are not included in the convolution calculation.")
         hx, hy, hw, wl, extent_out, projection, ill_count = \
             self._hit_detector(detector_index, source_index, extent, projection_method)
         det = self.detectors[detector_index]
@@ -407,11 +409,14 @@ class Raytracer(Group):
         if source_index is not None:
             desc = f"Rays from RS{source_index} at " + desc
         img = RenderImage(long_desc=desc, extent=extent_out, projection=projection)
+        img._limit = limit                      # enlarges the extent by 2.7 limit (render_image.py:250-252)
         img._fix_extent()
         Nx, Ny = img._grid()
         data, cnt = engine.render_xyzw(self._scene.lib, hx, hy, hw, wl, img.extent, Nx, Ny)
         img._data_dev, img._counts_dev = data, cnt
         img._ready = dist.allreduce_sum_async((data, cnt)) if data.is_cuda else None     # side stream, NCCL
+        if limit is not None and not dont_filter:
+            img._apply_rayleigh_filter()        # resolution filter on the reduced image (render_image.py:420-421)
         if ill_count:
             warning(f"{ill_count} rays ({100*ill_count/self.rays.N_global:.3g}% of all rays) were ill-conditioned for "
                     f"numerical hit finding at detector {detector_index}. Where and whether they intersect might be wrong.")
@@ -437,8 +442,6 @@ class Raytracer(Group):
             raise IndexError("Invalid source_index.")
         if not self.check_if_rays_are_current():
             raise RuntimeError("Tracing geometry/properties changed. Please retrace first.")
-        if limit is not None:
-            raise NotImplementedError("limit filter is outside the accelerated path")
         rs = self.ray_sources[source_index]
         b, e = self.rays._local_range(source_index)
         st = self.rays._dev
@@ -447,11 +450,14 @@ class Raytracer(Group):
         y = st.p[N*nt + b:N*nt + e]
         img = RenderImage(long_desc=f"{RaySource.abbr}{source_index} at z = {rs.pos[2]:.5g} mm",
                           extent=np.array(rs.extent[:4], dtype=np.float64), projection=None)
+        img._limit = limit
         img._fix_extent()
         Nx, Ny = img._grid()
         data, cnt = engine.render_xyzw(self._scene.lib, x, y, st.w[b:e], st.wl[b:e], img.extent, Nx, Ny)
         img._data_dev, img._counts_dev = data, cnt
         img._ready = dist.allreduce_sum_async((data, cnt)) if data.is_cuda else None
+        if limit is not None and not kwargs.get("_dont_filter", False):
+            img._apply_rayleigh_filter()
         return img
 
     def source_spectrum(self, source_index: int = 0, **kwargs) -> LightSpectrum:
@@ -490,8 +496,6 @@ class Raytracer(Group):
         limit = expand(limit, "limit")
         projection_method = expand(projection_method, "projection_method")
         extentc = list(expand(extent, "extent", scalar_list=True))
-        if any(l is not None for l in limit):
-            raise NotImplementedError("limit filter is outside the accelerated path")
 
         rays_step = self.ITER_RAYS_STEP
         iterations = max(1, int(N/rays_step))
@@ -546,6 +550,7 @@ class Raytracer(Group):
                     pname = f": {det.desc}" if det.desc != "" else ""
                     im = RenderImage(long_desc=f"{Detector.abbr}{detector_index[j]}{pname} at z = {det.pos[2]:.5g} mm",
                                      extent=np.array(extentc[j], dtype=np.float64), projection=proj)
+                    im._limit = limit[j]
                     im._fix_extent()
                     grids[j] = im._grid()
                     Nx, Ny = grids[j]
@@ -570,6 +575,10 @@ class Raytracer(Group):
         for j in range(nd):
             dist.allreduce_sum_(images[j]._data_dev)
             dist.allreduce_sum_(images[j]._counts_dev)
+        # the filter is applied to the finished images (raytracer.py:1268-1272)
+        for j in range(nd):
+            if limit[j] is not None:
+                images[j]._apply_rayleigh_filter()
         self._msgs = msgs_cum
         self._show_messages(N)
         return images

@@ -85,3 +85,49 @@ def test_get_after_trace(ot):
     assert _close(rgb.data, io.get(im.data, im.extent, "sRGB (Absolute RI)", 189))
     irr = im.get("Irradiance", 945)
     assert abs(irr.data.sum()*irr.Apx - im.power()) <= 1e-9*im.power()
+
+
+@pytest.mark.parametrize("scene", ["spherical_aberration", "image_render"])
+def test_resolution_filter_matches_reference(ot, scene):
+    """RenderImage.render(p, w, wl, limit) — binning + Airy-disc convolution on the device —
+    against the reference's output (FFT convolution on the host); direct vs FFT convolution differ by rounding"""
+    g = gu.load(scene)
+    gf = dict(np.load(gu.GOLDEN / f"filter_{scene}.npz"))
+    limit = float(gf["limit"])
+    img = ot.RenderImage(extent=g["det0_extent0"])
+    img.render(g["det0_ph"], g["det0_w"], g["det0_wl"], limit=limit)
+    assert img.limit == limit and np.allclose(img.extent, gf["extent"], rtol=0, atol=1e-12)
+    d = img.data
+    assert d.shape == tuple(int(v) for v in gf["shape"]) and d.min() >= 0
+    y0, x0 = [int(v) for v in gf["crop_origin"]]
+    scale = np.abs(gf["crop"]).max(axis=(0, 1))
+    assert np.all(np.abs(d[y0:y0 + 96, x0:x0 + 96] - gf["crop"]) <= 1e-9*scale)
+    assert np.allclose(d.sum(axis=(0, 1)), gf["sums"], rtol=1e-9)
+    assert _close(img.get("Irradiance", 189).data, gf["irr"])
+    # unfiltered render + explicit filter = filtered render; projected images refuse the filter
+    img2 = ot.RenderImage(extent=g["det0_extent0"])
+    img2.render(g["det0_ph"], g["det0_w"], g["det0_wl"], limit=limit, _dont_filter=True)
+    assert abs(img2.power() - float(np.sum(g["det0_w"].astype(np.float64)))) < 1e-9
+    img2._apply_rayleigh_filter()
+    assert np.array_equal(img2.data, d)
+    img3 = ot.RenderImage(extent=g["det0_extent0"], projection="Equidistant")
+    with pytest.raises(RuntimeError):
+        img3.render(g["det0_ph"], g["det0_w"], g["det0_wl"], limit=limit)
+
+
+def test_detector_image_and_iterative_render_with_limit(ot):
+    """limit= through Raytracer.detector_image / iterative_render: power is conserved by the normalised kernel
+    (up to what is convolved out of the enlarged extent), the extent grows by 2.7 limit, chunks are filtered once"""
+    import scenes
+    RT = scenes.spherical_aberration(ot)
+    ot.global_options.show_warnings = False
+    RT.trace(400_000)
+    plain = RT.detector_image()
+    filt = RT.detector_image(limit=40.0)
+    assert np.allclose(filt._extent0, plain._extent0)
+    assert np.allclose(filt.extent - plain.extent, np.array([-1, 1, -1, 1])*2.7*40.0/1000, atol=1e-12)
+    assert abs(filt.power() - plain.power()) < 1e-6*plain.power()
+    assert filt.data[:, :, 3].max() < plain.data[:, :, 3].max()           # blurred
+    RT.ITER_RAYS_STEP = 200_000
+    ims = RT.iterative_render(400_000, limit=40.0)
+    assert ims[0].limit == 40.0 and abs(ims[0].power() - plain.power()) < 2e-2*plain.power()

@@ -189,37 +189,42 @@ __global__ void __launch_bounds__(128, 6) detector_hits_kernel(const DetArgs a)
     }
 }
 
-// ---- render kernel: block-private hash table in shared memory ------------------------------------------------
+// ---- render kernel: warp-private hash tables in shared memory --------------------------------------------------
 // Detector images of imaging systems are PSF-like: the 7 M hits of the double-Gauss workload fall into 3e4 of
 // the 4.5 M pixels, 2e5 of them into the hottest one, and fp64 atomics on a handful of L2 addresses serialise.
-// Every block therefore accumulates its contiguous chunk of hits in a shared-memory hash table (pixel index ->
-// X, Y, Z, W sums and count; open addressing, 8 probes) after the warp-level aggregation of otb_bin.cuh, and
-// flushes the table with one global atomic per occupied slot and channel at the end.  Hits that find no slot
-// (spread images overflow the table) go to global memory directly, as before.
-#define OTB_RH_SLOTS 2048
+// After the warp-level aggregation of otb_bin.cuh (one leader lane per distinct pixel) every WARP accumulates
+// its hits in its own shared-memory hash table (pixel index -> X, Y, Z, W sums and count; open addressing,
+// 8 probes).  A table is only ever touched by the lanes of its warp and two leaders never hold the same pixel,
+// so the sums are plain read-modify-writes: no fp64 atomics (shared memory has none natively; a CAS loop per
+// channel was the bottleneck of a block-shared table).  Only claiming an empty slot is an atomic (two leaders of
+// the warp may race for it).  At the end every occupied slot is flushed with one global atomic per channel; hits
+// that find no slot (spread images overflow the table) go to global memory directly.
+#define OTB_RH_WARPS 8
+#define OTB_RH_SLOTS 256                       // per warp
 #define OTB_RH_PROBES 8
-#define OTB_RENDER_SMEM (OTB_RH_SLOTS*(4*sizeof(double) + 2*sizeof(int)))
+#define OTB_RENDER_SMEM (OTB_RH_WARPS*OTB_RH_SLOTS*(4*sizeof(double) + 2*sizeof(int)))
 
-__global__ void __launch_bounds__(256) render_kernel(BinGrid g, const double* __restrict__ obs, int64_t M,
+__global__ void __launch_bounds__(32*OTB_RH_WARPS) render_kernel(BinGrid g, const double* __restrict__ obs, int64_t M,
                                                      const double* __restrict__ x, const double* __restrict__ y,
                                                      const float* __restrict__ w, const float* __restrict__ wl,
                                                      double* __restrict__ img, int* __restrict__ cnt)
 {
-    extern __shared__ double rh_val[];                       // [4][SLOTS]
-    int* rh_key = (int*)(rh_val + 4*OTB_RH_SLOTS);           // [SLOTS], -1 = empty
-    int* rh_cnt = rh_key + OTB_RH_SLOTS;                     // [SLOTS]
-    for (int i = threadIdx.x; i < OTB_RH_SLOTS; i += blockDim.x) {
-        rh_key[i] = -1;
-        rh_cnt[i] = 0;
-        rh_val[i] = rh_val[i + OTB_RH_SLOTS] = rh_val[i + 2*OTB_RH_SLOTS] = rh_val[i + 3*OTB_RH_SLOTS] = 0.0;
+    extern __shared__ double rh_smem[];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* val = rh_smem + (size_t)warp*4*OTB_RH_SLOTS;                                  // [4][SLOTS] of this warp
+    int* key = (int*)(rh_smem + (size_t)OTB_RH_WARPS*4*OTB_RH_SLOTS) + warp*2*OTB_RH_SLOTS; // [SLOTS], -1 = empty
+    int* num = key + OTB_RH_SLOTS;                                                        // [SLOTS]
+    for (int i = lane; i < OTB_RH_SLOTS; i += 32) {
+        key[i] = -1;
+        num[i] = 0;
+        val[i] = val[i + OTB_RH_SLOTS] = val[i + 2*OTB_RH_SLOTS] = val[i + 3*OTB_RH_SLOTS] = 0.0;
     }
-    __syncthreads();
+    __syncwarp();
 
     // contiguous chunk per block (rays of one source are contiguous: fewer distinct pixels per table);
     // uniform trip count per warp: every lane takes part in the warp-level aggregation
-    const int64_t chunk = ((M + gridDim.x - 1)/gridDim.x + 255)/256*256;
+    const int64_t chunk = ((M + gridDim.x - 1)/gridDim.x + blockDim.x - 1)/blockDim.x*blockDim.x;
     const int64_t lo = (int64_t)blockIdx.x*chunk, hi = (lo + chunk < M) ? lo + chunk : M;
-    const unsigned lane = threadIdx.x & 31;
     for (int64_t base = lo; base < hi; base += blockDim.x) {
         const int64_t i = base + threadIdx.x;
         const bool in = i < hi;
@@ -235,21 +240,21 @@ __global__ void __launch_bounds__(256) render_kernel(BinGrid g, const double* __
         int n, pix;
         ok = aggregate_xyz_warp(g, ok, X, Y, wi, ox, oy, oz, lane, v0, v1, v2, v3, n, pix);
         if (ok) {
-            unsigned h = ((unsigned)pix*2654435761u) >> (32 - 11);          // Fibonacci hash, 2048 slots
+            unsigned h = ((unsigned)pix*2654435761u) >> (32 - 8);           // Fibonacci hash, 256 slots
             int slot = -1;
 #pragma unroll 1
             for (int t = 0; t < OTB_RH_PROBES; ++t) {
-                int k = ((volatile int*)rh_key)[h];
-                if (k == -1) k = atomicCAS(&rh_key[h], -1, pix), k = (k == -1) ? pix : k;
+                int k = ((volatile int*)key)[h];
+                if (k == -1) k = atomicCAS(&key[h], -1, pix), k = (k == -1) ? pix : k;
                 if (k == pix) { slot = (int)h; break; }
                 h = (h + 1) & (OTB_RH_SLOTS - 1);
             }
             if (slot >= 0) {
-                atomicAdd(&rh_val[slot], v0);
-                atomicAdd(&rh_val[slot + OTB_RH_SLOTS], v1);
-                atomicAdd(&rh_val[slot + 2*OTB_RH_SLOTS], v2);
-                atomicAdd(&rh_val[slot + 3*OTB_RH_SLOTS], v3);
-                atomicAdd(&rh_cnt[slot], n);
+                val[slot] += v0;
+                val[slot + OTB_RH_SLOTS] += v1;
+                val[slot + 2*OTB_RH_SLOTS] += v2;
+                val[slot + 3*OTB_RH_SLOTS] += v3;
+                num[slot] += n;
             } else {
                 double* q = img + 4*(int64_t)pix;
                 atomicAdd(q + 0, v0);
@@ -259,17 +264,17 @@ __global__ void __launch_bounds__(256) render_kernel(BinGrid g, const double* __
                 if (cnt) atomicAdd(cnt + pix, n);
             }
         }
+        __syncwarp();        // the table updates of this round are visible to the whole warp before the next one
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < OTB_RH_SLOTS; i += blockDim.x) {
-        const int pix = rh_key[i];
+    for (int i = lane; i < OTB_RH_SLOTS; i += 32) {
+        const int pix = key[i];
         if (pix >= 0) {
             double* q = img + 4*(int64_t)pix;
-            atomicAdd(q + 0, rh_val[i]);
-            atomicAdd(q + 1, rh_val[i + OTB_RH_SLOTS]);
-            atomicAdd(q + 2, rh_val[i + 2*OTB_RH_SLOTS]);
-            atomicAdd(q + 3, rh_val[i + 3*OTB_RH_SLOTS]);
-            if (cnt) atomicAdd(cnt + pix, rh_cnt[i]);
+            atomicAdd(q + 0, val[i]);
+            atomicAdd(q + 1, val[i + OTB_RH_SLOTS]);
+            atomicAdd(q + 2, val[i + 2*OTB_RH_SLOTS]);
+            atomicAdd(q + 3, val[i + 3*OTB_RH_SLOTS]);
+            if (cnt) atomicAdd(cnt + pix, num[i]);
         }
     }
 }

@@ -251,8 +251,10 @@ __device__ __forceinline__ void trace_step(const KScene& sc, const double* __res
 #ifndef OTB_NO_FAST_PATH
     const KSurface& S = sc.surf[st.surface];
     bool done = false;
-    if (st.role <= OTB_STEP_LENS_BACK && S.kind == OTB_SURF_CONIC && S.par[OTB_P_K] == 0.0)
-        done = fast_sphere_lens_step<POL>(sc, st, S, r, fl, status);
+    if (st.role <= OTB_STEP_LENS_BACK && S.kind == OTB_SURF_CONIC) {
+        if (S.par[OTB_P_K] == 0.0) done = fast_conic_lens_step<POL, true>(sc, st, S, r, fl, status);
+        else done = fast_conic_lens_step<POL, false>(sc, st, S, r, fl, status);
+    }
 #if OTB_STEP_OOL
     if (!done) {
         const StepIO o = trace_step_slow<POL, CAPS>(&sc, aux, &st, r, za, zb, status);
@@ -261,7 +263,7 @@ __device__ __forceinline__ void trace_step(const KScene& sc, const double* __res
     }
 #else
     if (done) return;
-    if (st.role <= OTB_STEP_LENS_BACK && S.kind == OTB_SURF_CONIC && S.par[OTB_P_K] == 0.0) {
+    if (st.role <= OTB_STEP_LENS_BACK && S.kind == OTB_SURF_CONIC) {
         const StepIO o = trace_step_slow<POL, CAPS>(&sc, aux, &st, r, za, zb, status);
         r = o.r;
         fl = o.fl;

@@ -257,10 +257,17 @@ __device__ inline V3 surf_normal(const KSurface& S, const double* __restrict__ a
             double rho2 = S.par[OTB_P_RHO2];
             return v3(-rho*dx, -rho*dy, sqrt(1 - rho2*(dx*dx) - rho2*(dy*dy)));
         }
+        // cos(phi), sin(phi) of phi = atan2(dy, dx) (conic_surface.py:104-110) taken as dx/r, dy/r: the same
+        // numbers to an ulp without three transcendental calls per ray; at the vertex phi = atan2(0, 0) = 0
         double r = sqrt(dx*dx + dy*dy);
-        double phi = atan2(dy, dx);
         double n_r = -rho*r/sqrt(1 - S.par[OTB_P_KRHO2]*(r*r));
-        return v3(n_r*cos(phi), n_r*sin(phi), sqrt(1 - n_r*n_r));
+        double c = 1.0, sn = 0.0;
+        if (r != 0.0) {
+            const double yr = rcp_seq(r);
+            c = div_seq(dx, r, yr);
+            sn = div_seq(dy, r, yr);
+        }
+        return v3(n_r*c, n_r*sn, sqrt(1 - n_r*n_r));
     }
     if (k == OTB_SURF_TILTED) return v3(S.par[OTB_P_NX], S.par[OTB_P_NY], S.par[OTB_P_NZ]);
 

@@ -254,6 +254,9 @@ __device__ __forceinline__ void trace_step(const KScene& sc, const double* __res
     if (st.role <= OTB_STEP_LENS_BACK && S.kind == OTB_SURF_CONIC) {
         if (S.par[OTB_P_K] == 0.0) done = fast_conic_lens_step<POL, true>(sc, st, S, r, fl, status);
         else done = fast_conic_lens_step<POL, false>(sc, st, S, r, fl, status);
+    } else if (st.role == OTB_STEP_APERTURE && !st.hurb && (S.flags & OTB_SF_FLAT) && !(S.flags & OTB_SF_ROTATED)
+               && (S.kind == OTB_SURF_CIRCLE || S.kind == OTB_SURF_RECT || S.kind == OTB_SURF_RING)) {
+        done = fast_flat_aperture_step(sc, S, r, fl);
     }
 #if OTB_STEP_OOL
     if (!done) {
@@ -263,7 +266,7 @@ __device__ __forceinline__ void trace_step(const KScene& sc, const double* __res
     }
 #else
     if (done) return;
-    if (st.role <= OTB_STEP_LENS_BACK && S.kind == OTB_SURF_CONIC) {
+    if ((st.role <= OTB_STEP_LENS_BACK && S.kind == OTB_SURF_CONIC) || st.role == OTB_STEP_APERTURE) {
         const StepIO o = trace_step_slow<POL, CAPS>(&sc, aux, &st, r, za, zb, status);
         r = o.r;
         fl = o.fl;

@@ -17,6 +17,11 @@ struct GenCtx {
     uint64_t m;        // index of the ray inside its source
     uint64_t n;        // rays of this source in this launch
     uint32_t src;      // source index (decorrelates sources)
+    // per-source constants, computed when the thread moves to another source
+    uint32_t fa, fb;   // moduli of the stratum permutation (feistel_setup)
+    uint64_t N2;       // floor(sqrt(n)): side of the stratified square grid (random.py:25-33)
+    double inv_n;      // 1 / n
+    Philox4 A, B;      // shared random blocks of this ray (see strat1)
 };
 
 enum { ST_POS = 1, ST_WL = 2, ST_RGB = 3, ST_DIV = 4, ST_DIV2 = 5, ST_POL = 6, ST_PIX = 7, ST_PIXOFF = 8 };
@@ -24,15 +29,23 @@ enum { ST_POS = 1, ST_WL = 2, ST_RGB = 3, ST_DIV = 4, ST_DIV2 = 5, ST_POL = 6, S
 __device__ __forceinline__ Philox4 draw(const GenCtx& g, uint32_t stream) { return philox4x32_10(g.gid, stream, g.src, g.seed); }
 __device__ __forceinline__ uint64_t stratum(const GenCtx& g, uint32_t stream)
 {
-    return feistel_perm(g.m, g.n, g.seed ^ ((uint64_t)stream << 40) ^ ((uint64_t)g.src << 20) ^ 0x5bd1e995u);
+    return feistel_perm_ab(g.m, g.n, g.fa, g.fb, g.seed ^ ((uint64_t)stream << 40) ^ ((uint64_t)g.src << 20) ^ 0x5bd1e995u);
 }
 
 // random.stratified_interval_sampling (random.py:48-66): value in [a, b)
+// One-dimensional draws need 64 of the 128 bits of a Philox block: wavelength + polarisation angle share block A,
+// RGB primary + image pixel share block B (both computed once per ray); the strata stay decorrelated through the
+// per-stream keys of the permutation.
 __device__ __forceinline__ double strat1(const GenCtx& g, uint32_t stream, double a, double b)
 {
-    Philox4 r = draw(g, stream);
-    double dba = (b - a)/(double)g.n;
-    return a + ((double)stratum(g, stream) + u01(r.v[0], r.v[1]))*dba;
+    uint32_t hi, lo;
+    if (stream == ST_WL) { hi = g.A.v[0]; lo = g.A.v[1]; }
+    else if (stream == ST_POL) { hi = g.A.v[2]; lo = g.A.v[3]; }
+    else if (stream == ST_RGB) { hi = g.B.v[0]; lo = g.B.v[1]; }
+    else if (stream == ST_PIX) { hi = g.B.v[2]; lo = g.B.v[3]; }
+    else { Philox4 r = draw(g, stream); hi = r.v[0]; lo = r.v[1]; }
+    double dba = (b - a)*g.inv_n;
+    return a + ((double)stratum(g, stream) + u01(hi, lo))*dba;
 }
 
 // random.stratified_rectangle_sampling (random.py:8-45)
@@ -40,9 +53,7 @@ __device__ __forceinline__ void strat2(const GenCtx& g, uint32_t stream, double 
 {
     Philox4 r = draw(g, stream);
     double u1 = u01(r.v[0], r.v[1]), u2 = u01(r.v[2], r.v[3]);
-    uint64_t N2 = (uint64_t)sqrt((double)g.n);
-    while (N2*N2 > g.n) --N2;
-    while ((N2 + 1)*(N2 + 1) <= g.n) ++N2;
+    const uint64_t N2 = g.N2;
     uint64_t j = stratum(g, stream);
     if (j < N2*N2) {
         uint64_t iy, ix;
@@ -152,16 +163,29 @@ generate_kernel(const __grid_constant__ GenArgs a)
     float* __restrict__ w0 = a.w0;
     float* __restrict__ wl0 = a.wl0;
     int* status = a.status;
+    GenCtx g;
+    int si_prev = -1;
     for (int64_t k = a.k_begin + (int64_t)blockIdx.x*blockDim.x + threadIdx.x; k < a.k_end; k += (int64_t)gridDim.x*blockDim.x) {
         int si = 0;
         for (int j = 1; j < nsrc; ++j) if (k >= a.src[j].ray_start) si = j;
         const OtbSource& S = a.src[si];
-        GenCtx g;
+        if (si != si_prev) {           // per-source constants
+            si_prev = si;
+            const uint64_t n = (uint64_t)S.n_rays;
+            feistel_setup(n, g.fa, g.fb);
+            uint64_t N2 = (uint64_t)sqrt((double)n);
+            while (N2*N2 > n) --N2;
+            while ((N2 + 1)*(N2 + 1) <= n) ++N2;
+            g.N2 = N2;
+            g.inv_n = 1.0/(double)n;
+        }
         g.seed = seed;
         g.gid = (uint64_t)(ray_offset + k);
         g.m = (uint64_t)(k - S.ray_start);
         g.n = (uint64_t)S.n_rays;
         g.src = (uint32_t)(a.src_index0 + si);
+        g.A = philox4x32_10(g.gid, 100u, g.src, g.seed);
+        if (S.shape > OTB_SHAPE_RECT) g.B = philox4x32_10(g.gid, 101u, g.src, g.seed);      // image sources only
 
         // ---- position (circular_surface.py:32-43, ring_surface.py:135-148, rectangular_surface.py:144-159,
         //      line.py:81-96, point.py:62-69, image sources ray_source.py:237-255)

@@ -79,16 +79,25 @@ __host__ __device__ __forceinline__ int bits_for(uint64_t n)      // smallest b 
 // never iterates.  (A power-of-two domain rejects up to half of the values, and a warp pays the MAXIMUM
 // iteration count of its 32 lanes: 6-7 walks of 4 rounds per permutation were 40 % of the generator.)
 // Larger n: balanced power-of-two Feistel with cycle walking.
-__host__ __device__ inline uint64_t feistel_perm(uint64_t i, uint64_t n, uint64_t key)
+// moduli of the generalised Feistel network for n < 2^31: a = ceil(sqrt(n)), b = ceil(n / a).  They depend on n
+// only; the generator computes them once per source, not once per ray and random variable.
+__host__ __device__ inline void feistel_setup(uint64_t n, uint32_t& a, uint32_t& b)
+{
+    a = b = 0;
+    if (n <= 1 || n >= 0x80000000ull) return;
+    const uint32_t n32 = (uint32_t)n;
+    a = (uint32_t)sqrtf((float)n32);
+    while ((uint64_t)a*a < n32) ++a;                 // float rounding repaired
+    while (a > 1 && (uint64_t)(a - 1)*(a - 1) >= n32) --a;
+    b = (n32 + a - 1)/a;
+}
+
+__host__ __device__ inline uint64_t feistel_perm_ab(uint64_t i, uint64_t n, uint32_t a, uint32_t b, uint64_t key)
 {
     if (n <= 1) return 0;
     const uint32_t ka = (uint32_t)key ^ (uint32_t)(key >> 32), kb = (uint32_t)(key >> 16) ^ (uint32_t)(key >> 32);
     if (n < 0x80000000ull) {
         const uint32_t n32 = (uint32_t)n;
-        uint32_t a = (uint32_t)sqrtf((float)n32);
-        while ((uint64_t)a*a < n32) ++a;                 // a = ceil(sqrt(n)), float rounding repaired
-        while (a > 1 && (uint64_t)(a - 1)*(a - 1) >= n32) --a;
-        const uint32_t b = (n32 + a - 1)/a;
         uint32_t x = (uint32_t)i;
         do {
             uint32_t R = x/a, L = x - R*a;               // L in Z_a, R in Z_b
@@ -122,4 +131,11 @@ __host__ __device__ inline uint64_t feistel_perm(uint64_t i, uint64_t n, uint64_
         x = ((uint64_t)l << half) | r;
     } while (x >= n);
     return x;
+}
+
+__host__ __device__ inline uint64_t feistel_perm(uint64_t i, uint64_t n, uint64_t key)
+{
+    uint32_t a, b;
+    feistel_setup(n, a, b);
+    return feistel_perm_ab(i, n, a, b, key);
 }

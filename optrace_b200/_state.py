@@ -18,3 +18,13 @@ def state_of(obj):
     if hasattr(obj, "__dict__") and type(obj).__module__.startswith("optrace_b200"):
         return (type(obj).__name__,) + tuple((k, state_of(v)) for k, v in obj.__dict__.items() if k not in ("desc", "long_desc"))
     return id(obj)      # callables, scipy spline objects, images
+
+
+# Scene epoch: bumped by every attribute assignment on a scene object (surfaces, elements, media, spectra).
+# Lets the Raytracer reuse its last structural state when nothing was assigned since (the deep walk above costs
+# ~0.1 ms and sits on the critical path between a synchronisation point and the next kernel launch).
+EPOCH = [0]
+
+
+def touch(*_):
+    EPOCH[0] += 1

@@ -15,6 +15,8 @@ from typing import Callable
 
 import numpy as np
 
+from . import _state
+
 from .options import global_options as go
 
 # OtbMediumModel
@@ -37,6 +39,10 @@ def wavelengths(N: int) -> np.ndarray:
 class _Described:
     def __init__(self, desc: str = "", long_desc: str = ""):
         self.desc, self.long_desc = desc, long_desc
+
+    def __setattr__(self, key, val):
+        object.__setattr__(self, key, val)
+        _state.EPOCH[0] += 1        # scene epoch: see _state.py
 
     def copy(self):
         return _copy.deepcopy(self)

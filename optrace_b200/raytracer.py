@@ -22,6 +22,7 @@ from .ray_storage import RayStorage, split_rays
 from .scene import flatten_raytracer, detector_record
 from .surfaces import RingSurface, SlitSurface, SphericalSurface
 from ._state import state_of
+from . import _state
 from . import color
 
 
@@ -90,17 +91,27 @@ class Raytracer(Group):
 
     # -- change detection (raytracer.py:141-179): structural hash of the flattened scene -------------
     def _geometry_state(self):
-        """plain-value state of everything the flattened scene depends on (no numpy work, ~0.1 ms)"""
+        """plain-value state of everything the flattened scene depends on.  The deep walk (~0.1 ms) is reused while
+        no attribute of any scene object was assigned (scene epoch, _state.py); positions are re-read every time
+        so that in-place edits of a `pos` array are still noticed."""
+        quick = (_state.EPOCH[0], len(self.elements), tuple(self.outline), self.no_pol, self.use_hurb, self.HURB_FACTOR,
+                 id(self.n0), tuple((id(el), el._front.pos.tobytes()) for el in self.elements))
+        cache = self.__dict__.get("_geom_cache")
+        if cache is not None and cache[0] == quick:
+            return cache[1]
         els = tuple((type(el).__name__, state_of(el._front), state_of(el._back), el._d1, el._d2,
                      state_of(getattr(el, "n", None)), state_of(getattr(el, "n2", None)),
                      state_of(getattr(el, "spectrum", None)), getattr(el, "D", None))
                     for el in self.elements if isinstance(el, (Lens, Filter, Aperture)))
-        return (els, tuple(self.outline), state_of(self.n0), self.no_pol, self.use_hurb, self.HURB_FACTOR)
+        key = (els, tuple(self.outline), state_of(self.n0), self.no_pol, self.use_hurb, self.HURB_FACTOR)
+        object.__setattr__(self, "_geom_cache", (quick, key))
+        return key
 
     def tracing_snapshot(self, scene_key=None):
         src = [(id(rs), tuple(rs.pos), rs.power, rs.divergence, rs.orientation, rs.polarization, rs.div_angle,
                 tuple(rs.s), tuple(rs.conv_pos), id(rs.spectrum)) for rs in self.ray_sources]
-        return dict(scene=self._geometry_state(), sources=src, rays=self.rays.crepr(),
+        return dict(scene=scene_key if scene_key is not None else self._geometry_state(), sources=src,
+                    rays=self.rays.crepr(),
                     settings=(self.no_pol, self.use_hurb, self.HURB_FACTOR))
 
     def check_if_rays_are_current(self) -> bool:
@@ -176,7 +187,15 @@ class Raytracer(Group):
             raise TypeError(f"N needs to be of type int, but is {type(N)}.")
         if N < 1:
             raise ValueError(f"Ray number N needs to be at least 1, but is {N}.")
-        self._geometry_checks()
+        # the checks depend on the geometry and the sources only: repeated traces of an unchanged scene reuse the
+        # verdict (the warnings were shown when it was computed)
+        ck = (self._geometry_state(), tuple((id(rs), rs._front.pos.tobytes()) for rs in self.ray_sources))
+        cache = self.__dict__.get("_check_cache")
+        if cache is not None and cache[0] == ck and not cache[1]:
+            self.geometry_error = False
+        else:
+            self._geometry_checks()
+            object.__setattr__(self, "_check_cache", (ck, bool(self.geometry_error)))
         if self.geometry_error and not self._ignore_geometry_error:
             warning("ABORTED TRACING")
             return True

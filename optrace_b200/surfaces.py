@@ -22,6 +22,7 @@ from typing import Callable
 import numpy as np
 
 from .options import warning
+from . import _state
 
 C_EPS = 1e-6    # Surface.C_EPS (surface.py:17)
 N_EPS = 1e-10   # Surface.N_EPS (surface.py:20)
@@ -46,6 +47,10 @@ class _Shape:
     def __init__(self, desc: str = "", long_desc: str = ""):
         self.desc = desc
         self.long_desc = long_desc
+
+    def __setattr__(self, key, val):
+        object.__setattr__(self, key, val)
+        _state.EPOCH[0] += 1        # scene epoch: see _state.py
 
     def copy(self):
         return _copy.deepcopy(self)

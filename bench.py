@@ -261,8 +261,8 @@ def run_gpu(args):
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kt]))
     power = img.power()
 
-    # for transparency: the same trace with the other engine build
-    other_ms = None
+    # for transparency: the same trace with the other engine build and with the opt-in relaxed arithmetic
+    other_ms = relaxed_ms = None
     if not args.no_compare and world == 1:
         try:
             RT.use_specialised_kernels = not specialised
@@ -277,6 +277,17 @@ def run_gpu(args):
         except Exception as e:      # informational leg only: never lose the measurement above
             print(f"[bench] comparison engine not timed: {e}", file=sys.stderr)
         RT.use_specialised_kernels = specialised
+        RT._scene, RT._scene_key = None, None
+        try:
+            RT.arithmetic = "relaxed"
+            kt.clear()
+            for k in range(4):
+                step_resident(k > 0)
+            torch.cuda.synchronize()
+            relaxed_ms = float(np.mean([a.elapsed_time(b) for a, b in kt]))
+        except Exception as e:
+            print(f"[bench] relaxed arithmetic not timed: {e}", file=sys.stderr)
+        RT.arithmetic = "exact"
         RT._scene, RT._scene_key = None, None
         if specialised:
             RT.compile()
@@ -362,7 +373,9 @@ def run_gpu(args):
                        "engine": ("scene-specialised trace kernel (Raytracer.compile(), cached nvcc build)" if specialised
                                   else "generic trace kernel"),
                        "trace_kernel_ms": kernel_ms,
-                       ("generic_trace_kernel_ms" if specialised else "specialised_trace_kernel_ms"): other_ms, "trace_only_ray_surfaces_per_s": n_local*world*(nt - 1)/(kernel_ms*1e-3),
+                       ("generic_trace_kernel_ms" if specialised else "specialised_trace_kernel_ms"): other_ms,
+                       "arithmetic": "exact (IEEE op-for-op, bit-identical to the reference on this scene)",
+                       "relaxed_arithmetic_trace_kernel_ms": relaxed_ms, "trace_only_ray_surfaces_per_s": n_local*world*(nt - 1)/(kernel_ms*1e-3),
                        "image_power_W": power},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved/peak_gbs,
                          "traffic": traffic, "traffic_source": "profiles/r1_trace_store_final_ncu.csv (ncu --set full, same workload)",

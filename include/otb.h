@@ -172,7 +172,15 @@ typedef struct OtbSceneDesc {
     const OtbMedium* media;
     const OtbFilter* filters;
     const double* aux;
+    int32_t arithmetic;    /* OTB_ARITH_*: floating-point contract of the lens-surface step */
+    int32_t pad;
 } OtbSceneDesc;
+
+/* OTB_ARITH_EXACT: every + - * / sqrt rounds like the reference's numpy float64 operation (results bit-identical
+ * on closed-form scenes).  OTB_ARITH_RELAXED: fused multiply-adds, reciprocal-multiply division, rsqrt-based
+ * square roots and normalisation; results within ~1e-14 of the reference (acceptance criterion: 1e-9). */
+#define OTB_ARITH_EXACT 0
+#define OTB_ARITH_RELAXED 1
 
 typedef struct OtbScene OtbScene;   /* opaque, device-resident copy of the descriptor */
 

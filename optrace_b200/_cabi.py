@@ -45,7 +45,7 @@ class OtbSceneDesc(C.Structure):
                 ("outline", C.c_double*6), ("hurb_factor", C.c_double),
                 ("surfaces", C.POINTER(OtbSurface)), ("steps", C.POINTER(OtbStep)),
                 ("media", C.POINTER(OtbMedium)), ("filters", C.POINTER(OtbFilter)),
-                ("aux", C.POINTER(C.c_double))]
+                ("aux", C.POINTER(C.c_double)), ("arithmetic", C.c_int32), ("pad", C.c_int32)]
 
 
 class OtbRays(C.Structure):

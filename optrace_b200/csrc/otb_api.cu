@@ -147,6 +147,7 @@ static void fill_kscene(const OtbSceneDesc* d, OtbScene* sc)
     k.no_pol = d->no_pol;
     k.medium0 = d->medium0;
     k.n_hurb = d->n_hurb;
+    k.arithmetic = d->arithmetic;
     for (int i = 0; i < 6; ++i) k.outline[i] = d->outline[i];
     k.hurb_factor = d->hurb_factor;
     for (int i = 0; i < d->n_steps; ++i) k.steps[i] = d->steps[i];

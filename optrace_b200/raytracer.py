@@ -36,6 +36,13 @@ class Raytracer(Group):
     """re-send scene and sampling tables host -> device on every trace even when unchanged (used by bench.py's
     end-to-end measurement, whose timed region must contain the host -> device copy of the step's inputs)"""
     use_specialised_kernels: bool = True
+    arithmetic: str = "exact"
+    """floating-point contract of the lens-surface step on the device.  "exact" (default): every + - * / sqrt rounds
+    like the reference's numpy float64 operation, results are bit-identical to the reference on closed-form
+    scenes.  "relaxed": fused multiply-adds, reciprocal-multiply division, rsqrt-based normalisation — 1.2x faster,
+    each operation within 1-2 ulp, but NOT a drop-in at the 1e-9 level: the reference's own sphere intersection
+    (B^2 - C) cancels 7 digits for sources tens of metres away, so any other rounding moves hit points by up to
+    ~1e-9 relative, and float32-stored weights / polarisation flip by a float32 ulp (6e-8)."""
     """use a cached scene-specialised engine build when one exists (see Raytracer.compile)"""
     ITER_RAYS_STEP: int = 8_000_000
     """rays per iterative_render chunk (reference: 1e6, raytracer.py:40; larger chunks keep all 148 SMs busy)"""
@@ -75,6 +82,8 @@ class Raytracer(Group):
             val = o
         elif key in ("no_pol", "use_hurb") and not isinstance(val, bool):
             raise TypeError(f"{key} needs to be bool.")
+        elif key == "arithmetic" and val not in ("exact", "relaxed"):
+            raise ValueError("arithmetic needs to be 'exact' or 'relaxed'.")
         object.__setattr__(self, key, val)
 
     @property
@@ -95,6 +104,7 @@ class Raytracer(Group):
         no attribute of any scene object was assigned (scene epoch, _state.py); positions are re-read every time
         so that in-place edits of a `pos` array are still noticed."""
         quick = (_state.EPOCH[0], len(self.elements), tuple(self.outline), self.no_pol, self.use_hurb, self.HURB_FACTOR,
+                 self.arithmetic,
                  id(self.n0), tuple((id(el), el._front.pos.tobytes()) for el in self.elements))
         cache = self.__dict__.get("_geom_cache")
         if cache is not None and cache[0] == quick:
@@ -103,7 +113,7 @@ class Raytracer(Group):
                      state_of(getattr(el, "n", None)), state_of(getattr(el, "n2", None)),
                      state_of(getattr(el, "spectrum", None)), getattr(el, "D", None))
                     for el in self.elements if isinstance(el, (Lens, Filter, Aperture)))
-        key = (els, tuple(self.outline), state_of(self.n0), self.no_pol, self.use_hurb, self.HURB_FACTOR)
+        key = (els, tuple(self.outline), state_of(self.n0), self.no_pol, self.use_hurb, self.HURB_FACTOR, self.arithmetic)
         object.__setattr__(self, "_geom_cache", (quick, key))
         return key
 

@@ -32,6 +32,7 @@ class FlatScene:
         self.aux = np.zeros(0, dtype=np.float64)
         self.outline = [0.0]*6
         self.no_pol = False
+        self.arithmetic = 0          # OTB_ARITH_EXACT / OTB_ARITH_RELAXED
         self.medium0 = 0
         self.n_hurb = 0
         self.hurb_factor = 2**0.5
@@ -123,6 +124,7 @@ class FlatScene:
         d.no_pol, d.medium0, d.n_hurb, d.n_aux = int(self.no_pol), self.medium0, self.n_hurb, self.aux.shape[0]
         d.outline[:] = self.outline
         d.hurb_factor = self.hurb_factor
+        d.arithmetic = int(self.arithmetic)
         d.surfaces, d.steps = C.cast(S, C.POINTER(_cabi.OtbSurface)), C.cast(ST, C.POINTER(_cabi.OtbStep))
         d.media, d.filters = C.cast(M, C.POINTER(_cabi.OtbMedium)), C.cast(F, C.POINTER(_cabi.OtbFilter))
         d.aux = aux.ctypes.data_as(C.POINTER(C.c_double))
@@ -135,7 +137,7 @@ class FlatScene:
         h = hashlib.sha256()
         # repr() of floats round-trips exactly, so hashing the record dicts is as strict as hashing the structs
         h.update(repr((self.surfaces, self.steps, self.media, self.filters, self.outline, self.hurb_factor,
-                       self.no_pol, self.medium0)).encode())
+                       self.no_pol, self.medium0, self.arithmetic)).encode())
         h.update(self.aux.tobytes())
         h.update(repr([(k, id(f), sorted(a.items())) for k, f, a in self.user_funcs]).encode())
         return h.hexdigest()
@@ -169,6 +171,7 @@ def flatten_raytracer(rt) -> FlatScene:
     o = rt.outline
     fs.outline = [float(v) for v in o]
     fs.no_pol = bool(rt.no_pol)
+    fs.arithmetic = 1 if getattr(rt, "arithmetic", "exact") == "relaxed" else 0
     fs.hurb_factor = float(rt.HURB_FACTOR)
     fs.medium0 = fs.add_medium(rt.n0)
 

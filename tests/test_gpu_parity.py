@@ -29,17 +29,21 @@ def ot():
     return ot
 
 
-def _trace_fixture(ot, name):
+def _trace_fixture(ot, name, arithmetic=None):
     g = gu.load(name)
     RT = scenes.SCENES[name](ot)
+    if arithmetic is not None:
+        RT.arithmetic = arithmetic
     p0, s0, pol0, w0, wl, hz = gu.bundle(g)
     RT.trace_rays(p0, s0, pol0, w0, wl, hurb_z=hz, N_list=g["N_list"])
     return RT, g
 
 
+@pytest.mark.parametrize("arithmetic", ["relaxed", "exact"])
 @pytest.mark.parametrize("name", NAMES)
-def test_trace_matches_reference(ot, name):
-    RT, g = _trace_fixture(ot, name)
+def test_trace_matches_reference(ot, name, arithmetic):
+    """both floating-point contracts of the lens step (Raytracer.arithmetic) against the reference's output"""
+    RT, g = _trace_fixture(ot, name, arithmetic)
     R = RT.rays
     assert R.p_list.shape == g["p_list"].shape and R.p_list.dtype == np.float64 and R.p_list.flags.f_contiguous
     assert R.w_list.dtype == np.float32 and R.n_list.dtype == np.float64 and R.wl_list.dtype == np.float32
@@ -51,9 +55,14 @@ def test_trace_matches_reference(ot, name):
         errs["pol"] = gu.vecrel(R.pol_list, g["pol_list"])
     else:
         assert np.all(np.isnan(R.pol_list))
-    print(name, {k: f"{v:.2e}" for k, v in errs.items()})
+    print(name, arithmetic, {k: f"{v:.2e}" for k, v in errs.items()})
     for k, v in errs.items():
-        assert v <= (gu.W_RTOL.get(name, RTOL) if k == "w" else RTOL), (k, v)
+        tol = gu.W_RTOL.get(name, RTOL) if k == "w" else RTOL
+        if arithmetic == "relaxed":
+            # opt-in mode, not the drop-in contract: float64 quantities inherit the conditioning of the reference's
+            # own formulas (sphere intersection from 50 m away: 7 digits cancel), float32 storage flips by one ulp
+            tol = max(tol, 2e-7) if k in ("w", "pol") else 2e-8
+        assert v <= tol, (k, v)
     assert np.array_equal(R.wl_list, g["wl"])
 
 
@@ -157,3 +166,28 @@ def test_specialised_kernels_are_bit_identical(ot, name):
         else:
             assert np.array_equal(a, b, equal_nan=True), k
     assert gu.vecrel(res[1][0], g["p_list"]) <= RTOL and np.array_equal(res[1][5][:, :0], res[1][5][:, :0])
+
+
+@pytest.mark.parametrize("name", ["double_gauss", "spherical_aberration", "image_render"])
+def test_exact_arithmetic_is_bit_identical_on_closed_form_scenes(ot, name):
+    """Raytracer.arithmetic = "exact": spherical / flat scenes without transcendental functions reproduce the
+    reference's float64 results bit for bit (positions, directions, weights, indices, polarisation, messages)"""
+    RT, g = _trace_fixture(ot, name, "exact")
+    R = RT.rays
+    assert np.array_equal(R.p_list, g["p_list"], equal_nan=True)
+    assert np.array_equal(R.s0_list, g["s_list"], equal_nan=True)
+    assert np.array_equal(R.w_list, g["w_list"]) and np.array_equal(R.n_list, g["n_list"])
+    if "pol_list" in g:
+        assert np.array_equal(R.pol_list, g["pol_list"], equal_nan=True)
+    assert np.array_equal(RT._msgs, g["msgs"])
+
+
+def test_relaxed_arithmetic_error_level(ot):
+    """the opt-in relaxed contract: every operation is accurate to 1-2 ulp; what differs from the reference is the
+    rounding of ill-conditioned expressions of the reference itself (documented in Raytracer.arithmetic)"""
+    RT, g = _trace_fixture(ot, "spherical_aberration", "relaxed")       # sources at 3 mm: well conditioned
+    R = RT.rays
+    assert gu.vecrel(R.p_list, g["p_list"]) < 1e-12 and gu.vecrel(R.s0_list, g["s_list"]) < 1e-12
+    assert np.array_equal(RT._msgs, g["msgs"])
+    RT, g = _trace_fixture(ot, "double_gauss", "relaxed")               # sources at 50 m
+    assert gu.vecrel(RT.rays.p_list, g["p_list"]) < 5e-9 and np.array_equal(RT._msgs, g["msgs"])

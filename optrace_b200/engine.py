@@ -62,6 +62,19 @@ def side_stream():
     return _side[d]
 
 
+_gen = {}
+
+
+def gen_stream():
+    """per-device stream of the ray generator: the bundle of the next trace does not depend on the detector kernels
+    of the previous one that may still be queued on the compute stream, so it is generated beside them"""
+    torch = _torch()
+    d = torch.cuda.current_device()
+    if d not in _gen:
+        _gen[d] = torch.cuda.Stream(device=d)
+    return _gen[d]
+
+
 _pinned_pool = {}
 
 

@@ -36,6 +36,8 @@ class Raytracer(Group):
     """re-send scene and sampling tables host -> device on every trace even when unchanged (used by bench.py's
     end-to-end measurement, whose timed region must contain the host -> device copy of the step's inputs)"""
     use_specialised_kernels: bool = True
+    overlap_generation: bool = True
+    """generate the bundle of a trace on a side stream (beside detector kernels still queued on the compute stream)"""
     arithmetic: str = "exact"
     """floating-point contract of the lens-surface step on the device.  "exact" (default): every + - * / sqrt rounds
     like the reference's numpy float64 operation, results are bit-identical to the reference on closed-form
@@ -296,7 +298,10 @@ class Raytracer(Group):
         """otb_generate_rays for the local shard [begin, end) of the global ray range"""
         torch = engine._torch()
         lib = engine.ensure_init()
-        recs, aux_d = self._generator_tables()
+        main = torch.cuda.current_stream()
+        gs = engine.gen_stream() if self.overlap_generation else main
+        with torch.cuda.stream(gs):
+            recs, aux_d = self._generator_tables()          # (re-)upload of the sampling tables on the same stream
         B_list = np.concatenate(([0], np.cumsum(N_list)))
         sl = dist.source_slices(B_list, begin, end)
         n = end - begin
@@ -318,15 +323,25 @@ class Raytracer(Group):
                       "pix_cdf_off", "pix_cdf_n", "pix_rgb_off", "srgb_off"):
                 setattr(S, f, int(r[f]))
         d = engine.device()
-        p0 = torch.empty(3*n, dtype=torch.float64, device=d)
-        s0 = torch.empty(3*n, dtype=torch.float64, device=d)
-        pol0 = None if self.no_pol else torch.empty(3*n, dtype=torch.float32, device=d)
-        w0 = torch.empty(n, dtype=torch.float32, device=d)
-        wl = torch.empty(n, dtype=torch.float32, device=d)
-        status = torch.zeros(1, dtype=torch.int32, device=d)
-        _cabi.check(lib.otb_generate_rays(arr, len(sl), engine.dptr(aux_d), n, seed, begin, int(self.no_pol),
-                                          engine.dptr(p0), engine.dptr(s0), engine.dptr(pol0), engine.dptr(w0),
-                                          engine.dptr(wl), engine.dptr(status), engine.stream_ptr()), lib)
+        # The generator runs on its own stream: the bundle does not depend on kernels of a previous
+        # detector_image() that may still be queued on the compute stream (render: latency-bound, generator:
+        # ALU-bound, they share the SMs well).  The compute stream waits for it before the trace kernel.
+        with torch.cuda.stream(gs):
+            p0 = torch.empty(3*n, dtype=torch.float64, device=d)
+            s0 = torch.empty(3*n, dtype=torch.float64, device=d)
+            pol0 = None if self.no_pol else torch.empty(3*n, dtype=torch.float32, device=d)
+            w0 = torch.empty(n, dtype=torch.float32, device=d)
+            wl = torch.empty(n, dtype=torch.float32, device=d)
+            status = torch.zeros(1, dtype=torch.int32, device=d)
+            _cabi.check(lib.otb_generate_rays(arr, len(sl), engine.dptr(aux_d), n, seed, begin, int(self.no_pol),
+                                              engine.dptr(p0), engine.dptr(s0), engine.dptr(pol0), engine.dptr(w0),
+                                              engine.dptr(wl), engine.dptr(status),
+                                              C.c_void_p(gs.cuda_stream)), lib)
+        if gs is not main:
+            main.wait_stream(gs)
+            for t in (p0, s0, pol0, w0, wl, status):
+                if t is not None:
+                    t.record_stream(main)       # consumed by the trace on the compute stream
         rays = engine.DeviceRays(n, p0, s0, pol0, w0, wl, None, seed, begin)
         rays.gen_status = status        # checked when the trace result is synchronised anyway
         return rays

@@ -141,6 +141,7 @@ class RenderImage:
         self._data_dev = None      # torch tensor (Ny, Nx, 4) float64 on the GPU
         self._counts_dev = None    # torch tensor (Ny, Nx) int32: ray counts per bin (parity checks)
         self._ready = None         # CUDA event: device image complete (side-stream all-reduce of the shards)
+        self._counts_local = False  # several GPUs: the count channel still holds this rank's shard only
         self._host_buf = None      # pinned staging tensor of an asynchronous download
         self._host_ready = None    # CUDA event: download complete
         self._limit = None
@@ -243,10 +244,15 @@ class RenderImage:
 
     @property
     def counts(self) -> np.ndarray:
-        """number of rays binned per pixel (int32), for count-exact parity checks"""
+        """number of rays binned per pixel (int32), for count-exact parity checks.  On several GPUs the first access
+        all-reduces the channel: a collective call, every rank has to make it."""
         if self._counts_dev is None:
             raise RuntimeError("No count channel rendered.")
         self._wait_device()
+        if self._counts_local:
+            from . import dist
+            dist.allreduce_sum_(self._counts_dev)
+            self._counts_local = False
         return self._counts_dev.cpu().numpy()
 
     @property

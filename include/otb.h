@@ -326,6 +326,24 @@ int otb_scene_destroy(OtbScene* scene);
  * re-upload the scene at every trace (the reference re-walks its object tree per trace, raytracer.py:297-305). */
 int otb_scene_update(OtbScene* scene, const OtbSceneDesc* desc, void* stream);
 
+/* ---- focus search: Raytracer.focus_search (raytracer.py:1354-1640) on device-resident rays ---------------------
+ * prepare: per ray of [ray_begin, ray_end) the section before the first stored point behind z and the line
+ *   hit(z') = (pax + sbx z', pay + sby z') through it, its float32 weight and a used flag (0: no such section);
+ *   n_use_d += number of used rays (raytracer.py:1553-1578, RayStorage.rays_by_mask ray_storage.py:235-293).
+ * moments: weighted sums over the used rays into out_d[4] (zeroed first); par_d = device array [z, ...]:
+ *   mode 0: [sum w, sum w^2, sum w x, sum w y] at z              (np.cov / np.average, raytracer.py:1376-1379, 1620)
+ *   mode 1: [sum w (x - par[1])^2, sum w (y - par[2])^2] at z
+ *   mode 2: the two sums of the direct RMS solution (raytracer.py:1430-1442) with pb0 = par[1:3], v/vz = par[3:5]
+ * image: rng_d[4] = range of the hit positions at z, img_d (npx, npx) = weighted histogram over that range
+ *   (raytracer.py:1387-1392, misc.binning_indices_2d misc.py:59-91). */
+int otb_focus_prepare(const OtbRayStore* store, int64_t ray_begin, int64_t ray_end, double z,
+                      double* pax_d, double* pay_d, double* sbx_d, double* sby_d, float* w_d, uint8_t* use_d,
+                      int64_t* n_use_d, void* stream);
+int otb_focus_moments(const double* pax_d, const double* pay_d, const double* sbx_d, const double* sby_d, const float* w_d,
+                      const uint8_t* use_d, int64_t n, int32_t mode, const double* par_d, double* out_d, void* stream);
+int otb_focus_image(const double* pax_d, const double* pay_d, const double* sbx_d, const double* sby_d, const float* w_d,
+                    const uint8_t* use_d, int64_t n, double z, int32_t npx, double* rng_d, double* img_d, void* stream);
+
 /* Resolution-limit filter, RenderImage._apply_rayleigh_filter (render_image.py:255-296): out = max(img (*) psf, 0),
  * zero padded "same" convolution of every XYZW channel with the host-built (K, K) Airy-disc table, K odd.
  * Replaces scipy.signal.fftconvolve of the reference's host path (direct convolution: the kernel is compact). */

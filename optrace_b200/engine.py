@@ -494,3 +494,45 @@ def image_convolve(data_dev, psf: np.ndarray):
     out = torch.empty_like(data_dev)
     check(lib.otb_image_convolve(dptr(data_dev), Ny, Nx, dptr(psf_d), int(psf.shape[0]), dptr(out), stream_ptr()), lib)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# focus search (Raytracer.focus_search, raytracer.py:1354-1640)
+# ---------------------------------------------------------------------------------------------------
+class FocusLines:
+    """device arrays of the auxiliary lines hit(z) = pa + sb z of the selected rays (otb_focus_prepare)"""
+
+    def __init__(self, lib, store: DeviceStore, begin: int, end: int, z: float):
+        torch = _torch()
+        d = device()
+        n = end - begin
+        self.lib, self.n = lib, n
+        self.pax, self.pay, self.sbx, self.sby = (torch.empty(max(n, 1), dtype=torch.float64, device=d) for _ in range(4))
+        self.w = torch.empty(max(n, 1), dtype=torch.float32, device=d)
+        self.use = torch.empty(max(n, 1), dtype=torch.uint8, device=d)
+        cnt = torch.zeros(1, dtype=torch.int64, device=d)
+        s = store.c_struct()
+        check(lib.otb_focus_prepare(C.byref(s), begin, end, float(z), dptr(self.pax), dptr(self.pay), dptr(self.sbx),
+                                    dptr(self.sby), dptr(self.w), dptr(self.use), dptr(cnt), stream_ptr()), lib)
+        self.n_use = int(cnt.item())
+        self._par = torch.zeros(5, dtype=torch.float64, device=d)
+        self._out = torch.zeros(4, dtype=torch.float64, device=d)
+        self._rng = torch.zeros(4, dtype=torch.float64, device=d)
+
+    def _args(self):
+        return (dptr(self.pax), dptr(self.pay), dptr(self.sbx), dptr(self.sby), dptr(self.w), dptr(self.use), self.n)
+
+    def moments(self, mode: int, par) -> np.ndarray:
+        torch = _torch()
+        p = np.zeros(5)
+        p[:len(par)] = par
+        self._par.copy_(torch.from_numpy(p))
+        check(self.lib.otb_focus_moments(*self._args(), mode, dptr(self._par), dptr(self._out), stream_ptr()), self.lib)
+        return self._out.cpu().numpy().copy()
+
+    def image(self, z: float, npx: int):
+        """(extent [x0, x1, y0, y1], weighted (npx, npx) histogram) of the hit positions at z"""
+        torch = _torch()
+        img = torch.empty((npx, npx), dtype=torch.float64, device=self.pax.device)
+        check(self.lib.otb_focus_image(*self._args(), float(z), npx, dptr(self._rng), dptr(img), stream_ptr()), self.lib)
+        return self._rng.cpu().numpy().copy(), img.cpu().numpy()

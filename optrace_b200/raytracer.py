@@ -518,6 +518,121 @@ class Raytracer(Group):
         return LightSpectrum.render(st.wl[b:e].cpu().numpy(), st.w[b:e].cpu().numpy(),
                                     long_desc=f"Spectrum of {RaySource.abbr}{source_index} at z = {rs.pos[2]:.5g} mm", **kwargs)
 
+    # -- focus search (raytracer.py:1354-1640) ---------------------------------------------------------------
+    focus_search_methods = ["RMS Spot Size", "Irradiance Variance", "Image Sharpness", "Image Center Sharpness"]
+
+    @staticmethod
+    def _focus_image_cost(mode: str, ext: np.ndarray, Im: np.ndarray) -> float:
+        """cost of one rendered N_px x N_px image (raytracer.py:1394-1420): O(N_px^2) host arithmetic"""
+        N_px = Im.shape[0]
+        if mode in ("Image Sharpness", "Image Center Sharpness"):
+            if mode == "Image Center Sharpness":
+                Y, X = np.mgrid[-1:1:N_px*1j, -1:1:N_px*1j]
+                R = np.sqrt(X**2 + Y**2)
+                win = np.where(R > 1, 0, 1 + np.cos(R*np.pi))
+                Im0 = Im*win
+                if (Im0s := Im0.sum()):
+                    Im0 *= 1/Im0s
+            else:
+                Im0 = Im
+            rsm = ((Im0[1:] - Im0[:-1])**2).sum() + ((Im0[:, 1:] - Im0[:, :-1])**2).sum()
+            return -rsm
+        Im = Im[Im > 0]
+        Ap = (ext[1] - ext[0])*(ext[3] - ext[2])/N_px**2
+        return -np.log(Im.var()/Ap**2)
+
+    def _focus_cost(self, L, z_pos: float, mode: str) -> float:
+        """Raytracer.__focus_search_cost_function (raytracer.py:1354-1420); per-ray sums and binning on the device"""
+        if mode == "RMS Spot Size":
+            sw, sw2, swx, swy = L.moments(0, [z_pos])
+            cx, cy, _, _ = L.moments(1, [z_pos, swx/sw, swy/sw])
+            fact = sw - sw2/sw                      # np.cov(..., aweights=w), ddof = 1
+            return float(np.sqrt(cx/fact + cy/fact))
+        N_px = 100*int(1 + np.sqrt(L.n_use)/1500)
+        N_px = N_px if N_px % 2 else N_px + 1
+        ext, Im = L.image(z_pos, N_px)
+        return float(self._focus_image_cost(mode, ext, Im))
+
+    def focus_search(self, method: str, z_start: float, source_index: int = None, return_cost: bool = False):
+        """Raytracer.focus_search (raytracer.py:1449-1640).  Bounds, sampling of the cost function and the scipy
+        optimisers are the reference's; every pass over the rays (section selection, weighted moments, cost images)
+        runs on the device (otb_focus_prepare / otb_focus_moments / otb_focus_image)."""
+        import scipy.optimize
+        if not (self.outline[4] <= z_start <= self.outline[5]):
+            raise ValueError(f"Starting position z_start={z_start} outside raytracer z-outline range {self.outline[4:]}.")
+        if method not in self.focus_search_methods:
+            raise ValueError(f"Invalid method '{method}', should be one of {self.focus_search_methods}.")
+        if not self.rays.N_global:
+            raise RuntimeError("No rays traced.")
+        if source_index is not None and source_index < 0:
+            raise IndexError(f"source_index needs to be >= 0, but is {source_index}")
+        if (source_index is not None and source_index > len(self.rays.N_list)) or len(self.rays.N_list) == 0:
+            raise IndexError(f"source_index={source_index} larger than number of simulated sources "
+                             f"({len(self.rays.N_list)}. Either the source was not added or the new geometry was "
+                             "not traced.")
+        if not self.check_if_rays_are_current():
+            raise RuntimeError("Tracing geometry/properties changed or last trace had errors. Please retrace first.")
+        if dist.world() > 1:
+            raise NotImplementedError("focus_search runs on the rays of one GPU; trace without torchrun")
+
+        # search bounds: between the surfaces around z_start (raytracer.py:1505-1518)
+        b0 = self.N_EPS + np.max([rs.extent[5] for rs in self.ray_sources])
+        b1 = self.outline[5] - self.N_EPS
+        for surf in self.tracing_surfaces:
+            if surf.z_max > z_start:
+                b1 = surf.z_min
+                break
+            b0 = surf.z_max
+        bounds = [b0, b1]
+        Nt = 320
+
+        b, e = self.rays._local_range(source_index)
+        L = engine.FocusLines(self._scene.lib, self.rays._dev, b, e, bounds[0] + self.N_EPS)
+        N_use = L.n_use
+        if N_use < 1000:
+            warning(f"WARNING: Less than 1000 rays for focus_search ({N_use}).")
+        if N_use <= 1:
+            return scipy.optimize.OptimizeResult(), dict(pos=[np.nan, np.nan, np.nan], bounds=bounds, z=np.full(Nt, np.nan),
+                                                         cost=np.full(Nt, np.nan), N=N_use)
+
+        r = vals = None
+        if return_cost or method in ("Image Sharpness", "Image Center Sharpness"):
+            # random.stratified_interval_sampling(bounds[0], bounds[1], Nt, shuffle=False) (random.py:48-66)
+            dba = (bounds[1] - bounds[0])/Nt
+            r = bounds[0] + (np.arange(Nt) + np.random.default_rng().uniform(0, 1, Nt))*dba
+            vals = np.array([self._focus_cost(L, float(z), method) for z in r])
+
+        if method == "RMS Spot Size":
+            # direct solution (raytracer.py:1422-1447), extended by ray weights
+            m0, m1 = L.moments(0, [bounds[0]]), L.moments(0, [bounds[1]])
+            pb0, pb1 = m0[2:4]/m0[0], m1[2:4]/m1[0]
+            vz = bounds[1] - bounds[0]
+            vx, vy = pb1[0] - pb0[0], pb1[1] - pb0[1]
+            dnorm, num, _, _ = L.moments(2, [0.0, pb0[0], pb0[1], vx/vz, vy/vz])
+            d = -num/dnorm if dnorm else np.mean(bounds)
+            res = scipy.optimize.OptimizeResult()
+            res.x = float(np.clip(d, bounds[0], bounds[1]))
+            res.fun = self._focus_cost(L, res.x, "RMS Spot Size")
+        else:
+            cost = lambda z, method: self._focus_cost(L, float(z[0]), method)  # noqa: E731
+            if method == "Irradiance Variance":
+                res = scipy.optimize.minimize(cost, np.mean(bounds), args=method, tol=None, callback=None,
+                                              options={'maxiter': 100}, bounds=[bounds], method="Nelder-Mead")
+            else:
+                res = scipy.optimize.minimize(cost, r[int(np.argmin(vals))], args=method, tol=None, callback=None,
+                                              options={'maxiter': 30}, bounds=[bounds], method="COBYLA")
+            res.x = float(res.x[0])
+
+        rrl = (res.x - bounds[0]) < 10*(bounds[1] - bounds[0])/Nt
+        rrr = (bounds[1] - res.x) < 10*(bounds[1] - bounds[0])/Nt
+        if rrl or rrr:
+            warning("Found minimum near search bounds, this can mean the focus is outside of the search range.")
+        m = L.moments(0, [res.x])
+        pos = (float(m[2]/m[0]), float(m[3]/m[0]), float(res.x))      # np.average(pa + sb*res.x, weights) with z = res.x
+        if not return_cost:
+            r = vals = None
+        return res, dict(pos=pos, bounds=bounds, z=r, cost=vals, N=N_use)
+
     # -- iterative render (raytracer.py:1134-1279) ---------------------------------------------------------
     def iterative_render(self, N, detector_index=0, limit=None, projection_method="Equidistant", pos=None, extent=None):
         if not self.ray_sources:

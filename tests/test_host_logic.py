@@ -224,3 +224,43 @@ def test_translator_rejects_unsupported_code():
         return np.fft.fft(x)
     with pytest.raises(NotImplementedError):
         userfunc.translate("surf2d", bad, {}, "f")
+
+
+def test_stratum_permutation_is_a_bijection(tmp_path):
+    """otb_rng.cuh feistel_perm (the stand-in for the reference's shuffle of stratified samples, random.py:41-45)
+    is host-callable: compiled with nvcc as host code it must map [0, n) onto itself for awkward n as well"""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not pathlib.Path(nvcc).exists():
+        pytest.skip("nvcc not available")
+    src = tmp_path / "perm.cu"
+    src.write_text(r'''
+#include <cstdio>
+#include <vector>
+#include <cmath>
+#include "otb_rng.cuh"
+int main() {
+    const unsigned long long ns[] = {2, 3, 5, 16, 17, 100, 1000, 4097, 65536, 65537, 1000003};
+    for (unsigned long long n : ns) {
+        std::vector<char> seen(n, 0);
+        double corr = 0;
+        for (unsigned long long i = 0; i < n; ++i) {
+            unsigned long long p = feistel_perm(i, n, 0x1234567890abcdefull);
+            if (p >= n || seen[p]) { printf("FAIL %llu\n", n); return 1; }
+            seen[p] = 1;
+            corr += (double)i*(double)p;
+        }
+        double mean = (n - 1)/2.0, var = ((double)n*n - 1)/12.0;
+        if (n > 1000 && std::fabs((corr/n - mean*mean)/var) > 0.05) { printf("CORR %llu\n", n); return 2; }
+    }
+    printf("OK\n");
+    return 0;
+}
+''')
+    exe = tmp_path / "perm"
+    r = subprocess.run([nvcc, "-x", "cu", "-I", str(ROOT / "optrace_b200" / "csrc"), "-o", str(exe), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "OK", out.stdout

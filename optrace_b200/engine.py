@@ -246,13 +246,15 @@ def trace_store(scene: SceneHandle, rays: DeviceRays, store: DeviceStore | None 
 
 
 def trace_render(scene: SceneHandle, rays: DeviceRays, det_recs: list, extents=None, grids=None, imgs=None,
-                 cnts=None, msgs=None):
+                 cnts=None, msgs=None, status=None):
     """otb_trace_render (fused trace + detector + binning, no per-surface storage).
 
     Bin mode: `extents` (list of [x0,x1,y0,y1]), `grids` (list of (Nx, Ny)), `imgs`/`cnts` (device tensors,
     accumulated in place).  Range mode (imgs is None): returns a (n_det, 4) device tensor with the hit ranges.
-    At most 8 detectors per launch."""
+    At most 8 detectors per launch.  `status`: device int32[1] the caller checks later (raise_status) — bin mode then
+    returns without synchronising the host."""
     torch = _torch()
+    deferred = status is not None
     n = len(det_recs)
     dets = (_cabi.OtbDetector*n)()
     from .scene import fill_detector
@@ -260,7 +262,8 @@ def trace_render(scene: SceneHandle, rays: DeviceRays, det_recs: list, extents=N
         fill_detector(dets[k], rec)
     if msgs is None:
         msgs = torch.zeros(_cabi.NMSG*scene.nt, dtype=torch.int64, device=device())
-    status = torch.zeros(1, dtype=torch.int32, device=device())
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=device())
     r = rays.c_struct()
     if imgs is None:
         rng = torch.tensor([np.inf, -np.inf, np.inf, -np.inf]*n, dtype=torch.float64, device=device())
@@ -275,7 +278,8 @@ def trace_render(scene: SceneHandle, rays: DeviceRays, det_recs: list, extents=N
     cp = (C.c_void_p*n)(*[t.data_ptr() for t in cnts]) if cnts is not None else None
     check(scene.lib.otb_trace_render(scene.handle, C.byref(r), n, dets, ext, nx, ny, ip, cp, None,
                                      dptr(msgs), dptr(status), stream_ptr()), scene.lib)
-    raise_status(int(status.item()))
+    if not deferred:
+        raise_status(int(status.item()))
     return msgs.view(_cabi.NMSG, scene.nt)
 
 

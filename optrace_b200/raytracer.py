@@ -669,6 +669,8 @@ class Raytracer(Group):
         scene = self._scene_handle()
         nt = scene.nt
         msgs_cum = np.zeros((len(self.INFOS), nt), dtype=int)
+        msgs_dev = None
+        status_dev = torch.zeros(1, dtype=torch.int32, device=engine.device())      # OR-ed by every chunk, checked once
         powers = [rs.power for rs in self.ray_sources]
         nd = len(pos)
         images = [None]*nd
@@ -694,6 +696,7 @@ class Raytracer(Group):
             self._trace_count += 1
             seed = (int(self.seed) << 20) + self._trace_count
             rays = self._generate(N_list, begin, end, seed)
+            status_dev.bitwise_or_(rays.gen_status)
             recs = det_records()
             if i == 0:
                 # auto extents from the first chunk (raytracer.py:1042-1046, 1262): range pass without binning
@@ -728,13 +731,17 @@ class Raytracer(Group):
                     scratch[j].zero_()
                 m = engine.trace_render(scene, rays, [recs[j] for j in grp], extents=[images[j].extent for j in grp],
                                         grids=[grids[j] for j in grp], imgs=[scratch[j] for j in grp],
-                                        cnts=[images[j]._counts_dev for j in grp])
+                                        cnts=[images[j]._counts_dev for j in grp], status=status_dev)
                 msgs = m if msgs is None else msgs
                 for j in grp:
                     # Imi._data *= rays_step / N ; DIm_res[j]._data += Imi._data   (raytracer.py:1257-1264)
                     images[j]._data_dev.add_(scratch[j], alpha=rays_step/N)
-            dist.allreduce_sum_(msgs)
-            msgs_cum += msgs.cpu().numpy().astype(int)
+            # messages are accumulated on the device: no host synchronisation per chunk, the next chunk's generation
+            # and trace are queued while this one runs
+            msgs_dev = msgs.clone() if msgs_dev is None else msgs_dev.add_(msgs)
+        dist.allreduce_sum_(msgs_dev)
+        msgs_cum += msgs_dev.cpu().numpy().astype(int)
+        engine.raise_status(int(status_dev.item()))
         for j in range(nd):
             dist.allreduce_sum_(images[j]._data_dev)
             dist.allreduce_sum_(images[j]._counts_dev)

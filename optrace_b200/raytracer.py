@@ -389,6 +389,9 @@ class Raytracer(Group):
         self._run_trace(scene, rays, N_list, N, 0)
 
     def _run_trace(self, scene, rays, N_list, N_global, begin):
+        # drop the previous ray storage first: its device blocks go back to the caching allocator and the new
+        # store (same size on a repeated trace) reuses them instead of a fresh cudaMalloc of many GB
+        self.rays = RayStorage()
         store, msgs, status = engine.trace_store(scene, rays, sync=False)
         dist.allreduce_sum_(msgs)
         gen_status = getattr(rays, "gen_status", None)

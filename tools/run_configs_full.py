@@ -52,7 +52,7 @@ def store_mode(name, scene, N, dets=(0,)):
     RT = scenes.SCENES[scene](ot)
     nt = len(RT.tracing_surfaces) + 2
     RT.trace(N)                                 # warm-up at full size (allocator growth, tables, image sources)
-    [RT.detector_image(d) for d in dets]
+    [RT.detector_image(d).power() for d in dets]
     sync()
     t0 = time.perf_counter()
     RT.trace(N)
@@ -68,7 +68,7 @@ def fused_mode(name, scene, N, pos, step):
     RT = scenes.SCENES[scene](ot)
     nt = len(RT.tracing_surfaces) + 2
     RT.ITER_RAYS_STEP = step
-    RT.iterative_render(2*step, pos=pos)         # warm-up
+    [im.power() for im in RT.iterative_render(2*step, pos=pos)]         # warm-up
     sync()
     t0 = time.perf_counter()
     ims = RT.iterative_render(N, pos=pos)

@@ -342,7 +342,8 @@ int otb_focus_prepare(const OtbRayStore* store, int64_t ray_begin, int64_t ray_e
 int otb_focus_moments(const double* pax_d, const double* pay_d, const double* sbx_d, const double* sby_d, const float* w_d,
                       const uint8_t* use_d, int64_t n, int32_t mode, const double* par_d, double* out_d, void* stream);
 int otb_focus_image(const double* pax_d, const double* pay_d, const double* sbx_d, const double* sby_d, const float* w_d,
-                    const uint8_t* use_d, int64_t n, double z, int32_t npx, double* rng_d, double* img_d, void* stream);
+                    const uint8_t* use_d, int64_t n, double z, int32_t npx, int32_t phase, double* rng_d, double* img_d,
+                    void* stream);   /* phase 0: range + histogram, 1: range only, 2: histogram over the range in rng_d */
 
 /* Resolution-limit filter, RenderImage._apply_rayleigh_filter (render_image.py:255-296): out = max(img (*) psf, 0),
  * zero padded "same" convolution of every XYZW channel with the host-built (K, K) Airy-disc table, K odd.

@@ -105,7 +105,7 @@ SYMBOLS = {
     "otb_focus_prepare": (C.c_int, [C.POINTER(OtbRayStore), C.c_int64, C.c_int64, C.c_double, _VP, _VP, _VP, _VP, _VP,
                                     _VP, _VP, _VP]),
     "otb_focus_moments": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, C.c_int32, _VP, _VP, _VP]),
-    "otb_focus_image": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, C.c_double, C.c_int32, _VP, _VP, _VP]),
+    "otb_focus_image": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, C.c_double, C.c_int32, C.c_int32, _VP, _VP, _VP]),
     "otb_image_convolve": (C.c_int, [_VP, C.c_int32, C.c_int32, _VP, C.c_int32, _VP, _VP]),
     "otb_image_rescale": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP]),
     "otb_image_stats": (C.c_int, [_VP, C.c_int64, C.c_int32, C.c_double, _VP, _VP]),

@@ -211,21 +211,27 @@ int otb_focus_moments(const double* pax_d, const double* pay_d, const double* sb
     return OTB_OK;
 }
 
-// rng_d[4] receives the hit range; img_d (npx*npx doubles) the weighted histogram over that range
+// phase 0: both passes; phase 1: only the hit range into rng_d[4]; phase 2: only the weighted histogram img_d
+// (npx*npx doubles) over the range found in rng_d (several GPUs: the caller all-reduces the range in between)
 int otb_focus_image(const double* pax_d, const double* pay_d, const double* sbx_d, const double* sby_d, const float* w_d,
-                    const uint8_t* use_d, int64_t n, double z, int32_t npx, double* rng_d, double* img_d, void* stream)
+                    const uint8_t* use_d, int64_t n, double z, int32_t npx, int32_t phase, double* rng_d, double* img_d,
+                    void* stream)
 {
-    if (!pax_d || !pay_d || !sbx_d || !sby_d || !w_d || !use_d || !rng_d || !img_d || n < 1 || npx < 1) {
+    if (!pax_d || !pay_d || !sbx_d || !sby_d || !w_d || !use_d || !rng_d || !img_d || n < 1 || npx < 1 || phase < 0 || phase > 2) {
         otb_set_error("invalid argument");
         return OTB_ERR_INVALID_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
     FocusLines L = {(double*)pax_d, (double*)pay_d, (double*)sbx_d, (double*)sby_d, (float*)w_d, (unsigned char*)use_d};
-    const double init[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
-    OTB_CUDA(cudaMemcpyAsync(rng_d, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    OTB_CUDA(cudaMemsetAsync(img_d, 0, sizeof(double)*(size_t)npx*npx, st));
-    focus_range_kernel<<<focus_grid(n), 256, 0, st>>>(L, n, z, rng_d);
-    focus_image_kernel<<<focus_grid(n), 256, 0, st>>>(L, n, z, rng_d, npx, img_d);
+    if (phase != 2) {
+        const double init[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
+        OTB_CUDA(cudaMemcpyAsync(rng_d, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        focus_range_kernel<<<focus_grid(n), 256, 0, st>>>(L, n, z, rng_d);
+    }
+    if (phase != 1) {
+        OTB_CUDA(cudaMemsetAsync(img_d, 0, sizeof(double)*(size_t)npx*npx, st));
+        focus_image_kernel<<<focus_grid(n), 256, 0, st>>>(L, n, z, rng_d, npx, img_d);
+    }
     OTB_CUDA(cudaGetLastError());
     return OTB_OK;
 }

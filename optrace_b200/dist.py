@@ -116,3 +116,14 @@ def broadcast_ints(a: np.ndarray, device) -> np.ndarray:
         td.broadcast(t, src=0)
         return t.cpu().numpy()
     return np.asarray(a, dtype=np.int64)
+
+
+def broadcast_floats(a: np.ndarray, device) -> np.ndarray:
+    """rank 0's float64 array to all ranks (random sampling positions that every rank has to share)"""
+    if is_dist() and world() > 1:
+        import torch
+        td = _td()
+        t = torch.as_tensor(np.asarray(a, dtype=np.float64), device=device)
+        td.broadcast(t, src=0)
+        return t.cpu().numpy()
+    return np.asarray(a, dtype=np.float64)

@@ -518,6 +518,9 @@ class FocusLines:
         s = store.c_struct()
         check(lib.otb_focus_prepare(C.byref(s), begin, end, float(z), dptr(self.pax), dptr(self.pay), dptr(self.sbx),
                                     dptr(self.sby), dptr(self.w), dptr(self.use), dptr(cnt), stream_ptr()), lib)
+        from . import dist
+        self._dist = dist
+        dist.allreduce_sum_(cnt)                     # several GPUs: every rank holds the lines of its shard
         self.n_use = int(cnt.item())
         self._par = torch.zeros(5, dtype=torch.float64, device=d)
         self._out = torch.zeros(4, dtype=torch.float64, device=d)
@@ -532,11 +535,18 @@ class FocusLines:
         p[:len(par)] = par
         self._par.copy_(torch.from_numpy(p))
         check(self.lib.otb_focus_moments(*self._args(), mode, dptr(self._par), dptr(self._out), stream_ptr()), self.lib)
+        self._dist.allreduce_sum_(self._out)
         return self._out.cpu().numpy().copy()
 
     def image(self, z: float, npx: int):
         """(extent [x0, x1, y0, y1], weighted (npx, npx) histogram) of the hit positions at z"""
         torch = _torch()
         img = torch.empty((npx, npx), dtype=torch.float64, device=self.pax.device)
-        check(self.lib.otb_focus_image(*self._args(), float(z), npx, dptr(self._rng), dptr(img), stream_ptr()), self.lib)
+        if self._dist.world() > 1:       # range of all shards first, then every shard bins over the common grid
+            check(self.lib.otb_focus_image(*self._args(), float(z), npx, 1, dptr(self._rng), dptr(img), stream_ptr()), self.lib)
+            self._dist.allreduce_range_(self._rng)
+            check(self.lib.otb_focus_image(*self._args(), float(z), npx, 2, dptr(self._rng), dptr(img), stream_ptr()), self.lib)
+            self._dist.allreduce_sum_(img)
+        else:
+            check(self.lib.otb_focus_image(*self._args(), float(z), npx, 0, dptr(self._rng), dptr(img), stream_ptr()), self.lib)
         return self._rng.cpu().numpy().copy(), img.cpu().numpy()

@@ -575,8 +575,6 @@ class Raytracer(Group):
                              "not traced.")
         if not self.check_if_rays_are_current():
             raise RuntimeError("Tracing geometry/properties changed or last trace had errors. Please retrace first.")
-        if dist.world() > 1:
-            raise NotImplementedError("focus_search runs on the rays of one GPU; trace without torchrun")
 
         # search bounds: between the surfaces around z_start (raytracer.py:1505-1518)
         b0 = self.N_EPS + np.max([rs.extent[5] for rs in self.ray_sources])
@@ -603,6 +601,8 @@ class Raytracer(Group):
             # random.stratified_interval_sampling(bounds[0], bounds[1], Nt, shuffle=False) (random.py:48-66)
             dba = (bounds[1] - bounds[0])/Nt
             r = bounds[0] + (np.arange(Nt) + np.random.default_rng().uniform(0, 1, Nt))*dba
+            if dist.world() > 1:         # every rank must evaluate the same positions (collectives inside the cost)
+                r = dist.broadcast_floats(r, engine.device())
             vals = np.array([self._focus_cost(L, float(z), method) for z in r])
 
         if method == "RMS Spot Size":

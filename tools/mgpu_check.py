@@ -38,6 +38,18 @@ for name in ("double_gauss", "image_render"):
     if rank == 0:
         print(f"{name}: world={world} N={N} hits={cnt} power={pw:.6f} fused power={ims[0].power():.6f} rel diff {rel:.2e} msgs={RT._msgs.sum(axis=1)}")
     assert rel < 2e-2
+# focus search on sharded rays: moments, ranges and cost images are all-reduced, every rank runs the same optimiser
+RT = scenes.SCENES["double_gauss"](ot)
+RT.trace(1_000_003)
+res, info = RT.focus_search("RMS Spot Size", 120.0)
+res2, info2 = RT.focus_search("Image Sharpness", 120.0)
+chk = torch.tensor([res.x, res.fun, float(info["N"]), res2.x], dtype=torch.float64, device="cuda")
+mx = chk.clone(); td.all_reduce(mx, op=td.ReduceOp.MAX)
+mn = chk.clone(); td.all_reduce(mn, op=td.ReduceOp.MIN)
+assert torch.equal(mx, mn), (mx, mn)
+assert 130 < res.x < 150 and info2["bounds"][0] <= res2.x <= info2["bounds"][1], (res.x, res2.x)
+if rank == 0:
+    print(f"focus_search: world={world} rms focus z={res.x:.6f} (spot {res.fun:.3e} mm, {info['N']} rays), sharpness focus z={res2.x:.4f}")
 td.barrier()
 if rank == 0:
     print("mgpu_check ok")

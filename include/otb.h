@@ -345,6 +345,18 @@ int otb_focus_image(const double* pax_d, const double* pay_d, const double* sbx_
                     const uint8_t* use_d, int64_t n, double z, int32_t npx, int32_t phase, double* rng_d, double* img_d,
                     void* stream);   /* phase 0: range + histogram, 1: range only, 2: histogram over the range in rng_d */
 
+/* ---- spectrum histograms: LightSpectrum.render (light_spectrum.py:40-79) behind Raytracer.detector_spectrum /
+ * source_spectrum (raytracer.py:1100-1132, 1311-1329) on device-resident wavelengths and weights -------------
+ * stats: count_d[0] += rays used, count_d[1] += rays with non-zero weight among them (the reference sizes the bin
+ *   number from np.count_nonzero(w)); range_d[2] (float32, caller initialises to +inf, -inf) = min / max wavelength.
+ *   positive_only != 0: only rays with w > 0 are used (the hit selection of _hit_detector, raytracer.py:1023-1024).
+ * hist: hist_d[nbins] (float64, accumulated) += weights binned with np.histogram's uniform-bin rule on the float32
+ *   edges edges_d[nbins + 1] the host built with np.linspace exactly like numpy does. */
+int otb_spectrum_stats(const float* wl_d, const float* w_d, int64_t M, int32_t positive_only, int64_t* count_d,
+                       float* range_d, void* stream);
+int otb_spectrum_hist(const float* wl_d, const float* w_d, int64_t M, int32_t positive_only, const float* edges_d,
+                      int32_t nbins, double* hist_d, void* stream);
+
 /* Resolution-limit filter, RenderImage._apply_rayleigh_filter (render_image.py:255-296): out = max(img (*) psf, 0),
  * zero padded "same" convolution of every XYZW channel with the host-built (K, K) Airy-disc table, K odd.
  * Replaces scipy.signal.fftconvolve of the reference's host path (direct convolution: the kernel is compact). */

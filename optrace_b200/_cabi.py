@@ -106,6 +106,8 @@ SYMBOLS = {
                                     _VP, _VP, _VP]),
     "otb_focus_moments": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, C.c_int32, _VP, _VP, _VP]),
     "otb_focus_image": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, C.c_double, C.c_int32, C.c_int32, _VP, _VP, _VP]),
+    "otb_spectrum_stats": (C.c_int, [_VP, _VP, C.c_int64, C.c_int32, _VP, _VP, _VP]),
+    "otb_spectrum_hist": (C.c_int, [_VP, _VP, C.c_int64, C.c_int32, _VP, C.c_int32, _VP, _VP]),
     "otb_image_convolve": (C.c_int, [_VP, C.c_int32, C.c_int32, _VP, C.c_int32, _VP, _VP]),
     "otb_image_rescale": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP]),
     "otb_image_stats": (C.c_int, [_VP, C.c_int64, C.c_int32, C.c_double, _VP, _VP]),

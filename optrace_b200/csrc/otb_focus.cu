@@ -200,12 +200,13 @@ static int focus_grid(int64_t n) { const int64_t b = (n + 255)/256, cap = 8LL*ot
 int otb_focus_moments(const double* pax_d, const double* pay_d, const double* sbx_d, const double* sby_d, const float* w_d,
                       const uint8_t* use_d, int64_t n, int32_t mode, const double* par_d, double* out_d, void* stream)
 {
-    if (!pax_d || !pay_d || !sbx_d || !sby_d || !w_d || !use_d || !par_d || !out_d || n < 1 || mode < 0 || mode > 2) {
+    if (!pax_d || !pay_d || !sbx_d || !sby_d || !w_d || !use_d || !par_d || !out_d || n < 0 || mode < 0 || mode > 2) {
         otb_set_error("invalid argument");
         return OTB_ERR_INVALID_ARG;
     }
     FocusLines L = {(double*)pax_d, (double*)pay_d, (double*)sbx_d, (double*)sby_d, (float*)w_d, (unsigned char*)use_d};
     OTB_CUDA(cudaMemsetAsync(out_d, 0, 4*sizeof(double), (cudaStream_t)stream));
+    if (n == 0) return OTB_OK;      // empty shard (multi-GPU: this rank holds no ray of the selected source): zero sums
     focus_moments_kernel<<<focus_grid(n), 256, 0, (cudaStream_t)stream>>>(L, n, mode, par_d, out_d);
     OTB_CUDA(cudaGetLastError());
     return OTB_OK;
@@ -217,20 +218,22 @@ int otb_focus_image(const double* pax_d, const double* pay_d, const double* sbx_
                     const uint8_t* use_d, int64_t n, double z, int32_t npx, int32_t phase, double* rng_d, double* img_d,
                     void* stream)
 {
-    if (!pax_d || !pay_d || !sbx_d || !sby_d || !w_d || !use_d || !rng_d || !img_d || n < 1 || npx < 1 || phase < 0 || phase > 2) {
+    if (!pax_d || !pay_d || !sbx_d || !sby_d || !w_d || !use_d || !rng_d || !img_d || n < 0 || npx < 1 || phase < 0 || phase > 2) {
         otb_set_error("invalid argument");
         return OTB_ERR_INVALID_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
     FocusLines L = {(double*)pax_d, (double*)pay_d, (double*)sbx_d, (double*)sby_d, (float*)w_d, (unsigned char*)use_d};
+    // n == 0 is a valid empty shard (multi-GPU: no ray of the selected source on this rank): the range stays at its
+    // neutral element, the histogram at zero, and the caller's collectives still line up across ranks
     if (phase != 2) {
-        const double init[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
+        static const double init[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
         OTB_CUDA(cudaMemcpyAsync(rng_d, init, sizeof(init), cudaMemcpyHostToDevice, st));
-        focus_range_kernel<<<focus_grid(n), 256, 0, st>>>(L, n, z, rng_d);
+        if (n > 0) focus_range_kernel<<<focus_grid(n), 256, 0, st>>>(L, n, z, rng_d);
     }
     if (phase != 1) {
         OTB_CUDA(cudaMemsetAsync(img_d, 0, sizeof(double)*(size_t)npx*npx, st));
-        focus_image_kernel<<<focus_grid(n), 256, 0, st>>>(L, n, z, rng_d, npx, img_d);
+        if (n > 0) focus_image_kernel<<<focus_grid(n), 256, 0, st>>>(L, n, z, rng_d, npx, img_d);
     }
     OTB_CUDA(cudaGetLastError());
     return OTB_OK;

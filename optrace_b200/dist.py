@@ -15,7 +15,24 @@ def _td():
     return td
 
 
+_force_local = False     # tests: run one rank of an initialised job as if it were alone (reference result on one GPU)
+
+
+class local_mode:
+    """context manager: inside, this process behaves like a single-GPU job (no sharding, no collectives)"""
+
+    def __enter__(self):
+        global _force_local
+        self._old, _force_local = _force_local, True
+
+    def __exit__(self, *a):
+        global _force_local
+        _force_local = self._old
+
+
 def is_dist() -> bool:
+    if _force_local:
+        return False
     td = _td()
     return td.is_available() and td.is_initialized()
 
@@ -97,6 +114,41 @@ def allreduce_range_(rng):
     return rng
 
 
+STATUS_BITS = 5      # OTB_STATUS_* bits of include/otb.h
+
+
+def reduce_msgs_status(msgs, status):
+    """Message counters (SUM) and the device status word (bitwise OR) of all ranks with ONE collective and ONE
+    host synchronisation: the status bits travel bit-expanded behind the counters (NCCL has no bitwise reduction),
+    so every rank raises the same exception instead of one rank raising while the others wait in the next
+    collective.  Returns (msgs ndarray like the input shape, status int)."""
+    import torch
+    shape = tuple(msgs.shape)
+    if is_dist() and world() > 1:
+        td = _td()
+        bits = (status.to(torch.int64).reshape(1) >> torch.arange(STATUS_BITS, device=status.device)) & 1
+        buf = torch.cat((msgs.reshape(-1).to(torch.int64), bits))
+        td.all_reduce(buf, op=td.ReduceOp.SUM)
+        h = buf.cpu().numpy()
+        st = int(sum((1 << i) for i in range(STATUS_BITS) if h[-STATUS_BITS + i] > 0))
+        return h[:-STATUS_BITS].reshape(shape).astype(int), st
+    buf = torch.cat((msgs.reshape(-1).to(torch.int64), status.to(torch.int64).reshape(1)))
+    h = buf.cpu().numpy()
+    return h[:-1].reshape(shape).astype(int), int(h[-1])
+
+
+def gather_rows(t):
+    """small per-rank record (1-D tensor) -> host ndarray (world, len) with one collective and one host
+    synchronisation; the caller reduces the rows itself (min / max / sum / or per field)"""
+    if is_dist() and world() > 1:
+        import torch
+        td = _td()
+        out = torch.empty((world(), t.numel()), dtype=t.dtype, device=t.device)
+        td.all_gather_into_tensor(out, t.reshape(1, -1).contiguous())
+        return out.cpu().numpy()
+    return t.reshape(1, -1).cpu().numpy()
+
+
 def allreduce_max_scalar(v: float, device) -> float:
     if is_dist() and world() > 1:
         import torch
@@ -116,6 +168,17 @@ def broadcast_ints(a: np.ndarray, device) -> np.ndarray:
         td.broadcast(t, src=0)
         return t.cpu().numpy()
     return np.asarray(a, dtype=np.int64)
+
+
+def shared_split(N: int, powers, device) -> np.ndarray:
+    """rays per source, identical on every rank (RayStorage.init, ray_storage.py:56-68).  The split is deterministic
+    unless N does not divide by the power ratios: only then the remainder is drawn with np.random.choice and rank
+    0's draw is broadcast (a collective plus a host synchronisation that the common case does not pay)."""
+    from .ray_storage import split_rays
+    P = np.asarray(powers, dtype=np.float64)
+    if N - int(np.sum((N*P/np.sum(P)).astype(int))) == 0:
+        return split_rays(N, powers)
+    return broadcast_ints(split_rays(N, powers), device)
 
 
 def broadcast_floats(a: np.ndarray, device) -> np.ndarray:

@@ -269,7 +269,8 @@ def trace_render(scene: SceneHandle, rays: DeviceRays, det_recs: list, extents=N
         rng = torch.tensor([np.inf, -np.inf, np.inf, -np.inf]*n, dtype=torch.float64, device=device())
         check(scene.lib.otb_trace_render(scene.handle, C.byref(r), n, dets, None, None, None, None, None, dptr(rng),
                                          dptr(msgs), dptr(status), stream_ptr()), scene.lib)
-        raise_status(int(status.item()))
+        if not deferred:
+            raise_status(int(status.item()))
         return rng.view(n, 4)
     ext = (C.c_double*(4*n))(*[float(v) for e in extents for v in e])
     nx = (C.c_int32*n)(*[int(g[0]) for g in grids])
@@ -333,9 +334,17 @@ def detector_hits(lib, store: DeviceStore, det_rec: dict, ray_begin: int = 0, ra
 
 
 def read_det_meta(meta):
-    """(range ndarray[4], ill count, status) from the scratch record of detector_hits: one synchronising copy"""
-    m = meta.cpu()
-    return m[:4].numpy().copy(), int(m[4:5].view(_torch().int64).item()), int(m[5:6].view(_torch().int32)[0].item())
+    """(range ndarray[4], ill count, status) from the scratch records of detector_hits of ALL ranks: one all-gather
+    of the 48-byte record (none on a single GPU), one synchronising copy, reduced on the host — hit range MIN / MAX
+    (auto extent, raytracer.py:1042-1046), ill-conditioned count SUM, status bits OR"""
+    from . import dist
+    rows = dist.gather_rows(meta)                   # (world, 6) float64
+    r = np.array([rows[:, 0].min(), rows[:, 1].max(), rows[:, 2].min(), rows[:, 3].max()])
+    ill = int(rows[:, 4].copy().view(np.int64).sum())
+    st = 0
+    for v in rows[:, 5].copy().view(np.int32).reshape(-1, 2)[:, 0]:
+        st |= int(v)
+    return r, ill, st
 
 
 def render_xyzw(lib, x, y, w, wl, extent, Nx: int, Ny: int, img=None, cnt=None):
@@ -498,6 +507,41 @@ def image_convolve(data_dev, psf: np.ndarray):
     out = torch.empty_like(data_dev)
     check(lib.otb_image_convolve(dptr(data_dev), Ny, Nx, dptr(psf_d), int(psf.shape[0]), dptr(out), stream_ptr()), lib)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# spectrum histograms (LightSpectrum.render, light_spectrum.py:40-79)
+# ---------------------------------------------------------------------------------------------------
+def spectrum_histogram(lib, wl, w, positive_only: bool, wavelength_range):
+    """(vals float64[N], edges float32[N + 1]) of the weighted wavelength histogram of device tensors wl, w
+    (float32).  Bin count, range and float32 edges follow LightSpectrum.render / np.histogram; the counts and the
+    range of all ranks are combined with one all-gather, the bin sums with one all-reduce."""
+    torch = _torch()
+    from . import dist
+    d = device()
+    M = int(wl.shape[0])
+    rec = torch.zeros(4, dtype=torch.int64, device=d)         # [used, non-zero, (min, max) as two float32]
+    rng = rec[2:3].view(torch.float32)
+    rng.copy_(torch.tensor([np.inf, -np.inf], dtype=torch.float32))
+    check(lib.otb_spectrum_stats(dptr(wl), dptr(w), M, int(positive_only), dptr(rec), dptr(rng), stream_ptr()), lib)
+    rows = dist.gather_rows(rec)                               # one collective, one host synchronisation
+    used, nz = int(rows[:, 0].sum()), int(rows[:, 1].sum())
+    fr = rows[:, 2].copy().view(np.float32).reshape(-1, 2)
+    N = max(51, np.sqrt(nz)/2)
+    N = 1 + 2*(int(N)//2)
+    if not used:
+        return None, N
+    wl0, wl1 = np.float32(fr[:, 0].min()), np.float32(fr[:, 1].max())
+    if np.abs(wl0 - wl1) < 1:
+        wl0, wl1 = max(wl0 - 1, wavelength_range[0]), min(wl0 + 1, wavelength_range[1])
+    # the edges numpy itself would use (np.histogram -> _get_bin_edges -> np.linspace in the promoted dtype)
+    edges = np.histogram_bin_edges(np.array([wl0, wl1], dtype=np.float32), bins=N, range=[wl0, wl1])
+    edges32 = np.ascontiguousarray(edges, dtype=np.float32)
+    e_d = torch.from_numpy(edges32).to(d)
+    hist = torch.zeros(N, dtype=torch.float64, device=d)
+    check(lib.otb_spectrum_hist(dptr(wl), dptr(w), M, int(positive_only), dptr(e_d), N, dptr(hist), stream_ptr()), lib)
+    dist.allreduce_sum_(hist)
+    return hist.cpu().numpy(), edges
 
 
 # ---------------------------------------------------------------------------------------------------

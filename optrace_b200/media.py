@@ -374,3 +374,20 @@ class LightSpectrum(Spectrum):
             spec._vals, spec._wls = np.histogram(wl, bins=N, weights=w, range=[wl0, wl1])
             spec._vals = spec._vals*(1/(spec._wls[1] - spec._wls[0]))
         return spec
+
+    @staticmethod
+    def _render_device(lib, wl, w, positive_only: bool, **kwargs) -> "LightSpectrum":
+        """LightSpectrum.render on device-resident float32 wavelengths / weights (engine.spectrum_histogram):
+        same bin count, range, float32 edges and index rule as the host path above; bin sums accumulate in float64
+        on the device (the reference accumulates 65536-ray blocks in float32, np.histogram with float32 weights)."""
+        from . import engine
+        spec = LightSpectrum("Histogram", **kwargs)
+        vals, edges = engine.spectrum_histogram(lib, wl, w, positive_only, go.wavelength_range)
+        if vals is None:
+            N = edges
+            spec._wls = wavelengths(N + 1)
+            spec._vals = np.zeros(N, dtype=np.float64)
+        else:
+            spec._wls = edges
+            spec._vals = vals.astype(np.float32)*(1/(spec._wls[1] - spec._wls[0]))
+        return spec

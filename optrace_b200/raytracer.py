@@ -361,7 +361,7 @@ class Raytracer(Group):
             raise RuntimeError(f"More than {self.MAX_RAY_STORAGE_RAM*1e-9:.1f} GB RAM requested. Either decrease"
                                " the number of rays, surfaces or do an iterative render. If your system can handle"
                                " more RAM usage, increase the Raytracer.MAX_RAY_STORAGE_RAM parameter.")
-        N_list = dist.broadcast_ints(split_rays(N, [rs.power for rs in self.ray_sources]), engine.device())
+        N_list = dist.shared_split(N, [rs.power for rs in self.ray_sources], engine.device())
         if np.any(N_list == 0):
             warning("There are RaySources that have no rays assigned. "
                     "Change the power ratio or raise the overall ray number")
@@ -393,12 +393,13 @@ class Raytracer(Group):
         # store (same size on a repeated trace) reuses them instead of a fresh cudaMalloc of many GB
         self.rays = RayStorage()
         store, msgs, status = engine.trace_store(scene, rays, sync=False)
-        dist.allreduce_sum_(msgs)
         gen_status = getattr(rays, "gen_status", None)
         if gen_status is not None:
             status = status | gen_status
-        self._msgs = msgs.cpu().numpy().astype(int)     # the one host synchronisation of a trace
-        engine.raise_status(int(status.item()))
+        # the one collective and the one host synchronisation of a trace: message counters summed, status words
+        # OR-ed over all ranks, so that every rank raises the same exception
+        self._msgs, st = dist.reduce_msgs_status(msgs, status)
+        engine.raise_status(st)
         self.rays = RayStorage()
         self.rays._attach(store, self.ray_sources, N_list, self.no_pol, N_global, begin)
         self._show_messages(N_global)
@@ -428,11 +429,10 @@ class Raytracer(Group):
         b, e = self.rays._local_range(source_index)
         lib = self._scene.lib
         hx, hy, hw, rng, ill, status, meta = engine.detector_hits(lib, self.rays._dev, rec, b, e)
-        dist.allreduce_sum_(ill)
         projection = projection_method if rec["projection"] else None
-        if extent is None:
-            dist.allreduce_range_(rng)
-        r, ill_count, st = engine.read_det_meta(meta)      # the one host synchronisation of this call
+        # hit range (MIN / MAX), ill-conditioned count (SUM) and status (OR) of all ranks: one all-gather of the
+        # 48-byte record and the one host synchronisation of this call, reduced on the host
+        r, ill_count, st = engine.read_det_meta(meta)
         if extent is not None:
             extent_out = np.asarray_chkfinite(np.array(extent, dtype=np.float64))
         else:
@@ -473,14 +473,18 @@ class Raytracer(Group):
         return img
 
     def detector_spectrum(self, detector_index: int = 0, source_index: int = None, extent=None, **kwargs) -> LightSpectrum:
-        """Raytracer.detector_spectrum (raytracer.py:1100-1132); histogram of the hit wavelengths (host, 1-D)"""
-        hx, hy, hw, wl, _, _, _ = self._hit_detector(detector_index, source_index, extent)
-        m = hw > 0
+        """Raytracer.detector_spectrum (raytracer.py:1100-1132); weighted histogram of the hit wavelengths on the
+        device (otb_spectrum_stats / otb_spectrum_hist), counts, range and bin sums reduced over all GPUs"""
+        hx, hy, hw, wl, _, _, ill_count = self._hit_detector(detector_index, source_index, extent)
         det = self.detectors[detector_index]
         pname = f": {det.desc}" if det.desc != "" else ""
         desc = f"{Detector.abbr}{detector_index}{pname} at z = {det.pos[2]:.5g} mm"
         desc = (f"Spectrum of RS{source_index} at " if source_index is not None else "Spectrum at ") + desc
-        return LightSpectrum.render(wl[m].cpu().numpy(), hw[m].cpu().numpy(), long_desc=desc, **kwargs)
+        spec = LightSpectrum._render_device(self._scene.lib, wl, hw, True, long_desc=desc, **kwargs)
+        if ill_count:
+            warning(f"{ill_count} rays ({100*ill_count/self.rays.N_global:.3g}% of all rays) were ill-conditioned for "
+                    f"numerical hit finding at detector {detector_index}. Where and whether they intersect might be wrong.")
+        return spec
 
     def source_image(self, source_index: int = 0, limit: float = None, **kwargs) -> RenderImage:
         """Raytracer.source_image (raytracer.py:1331-1352)"""
@@ -512,14 +516,22 @@ class Raytracer(Group):
         return img
 
     def source_spectrum(self, source_index: int = 0, **kwargs) -> LightSpectrum:
-        """Raytracer.source_spectrum (raytracer.py:1311-1329)"""
+        """Raytracer.source_spectrum (raytracer.py:1311-1329), binned on the device like detector_spectrum"""
+        if not self.ray_sources:
+            raise RuntimeError("Ray Sources Missing.")
         if not self.rays.N_global:
             raise RuntimeError("No rays traced.")
+        if source_index > len(self.ray_sources) - 1 or source_index < 0:
+            raise IndexError("Invalid source_index.")
+        if not self.check_if_rays_are_current():
+            raise RuntimeError("Tracing geometry/properties changed. Please retrace first.")
         b, e = self.rays._local_range(source_index)
         st = self.rays._dev
         rs = self.ray_sources[source_index]
-        return LightSpectrum.render(st.wl[b:e].cpu().numpy(), st.w[b:e].cpu().numpy(),
-                                    long_desc=f"Spectrum of {RaySource.abbr}{source_index} at z = {rs.pos[2]:.5g} mm", **kwargs)
+        pname = f": {rs.desc}" if rs.desc != "" else ""
+        return LightSpectrum._render_device(self._scene.lib, st.wl[b:e], st.w[b:e], False,
+                                            long_desc=f"Spectrum of {RaySource.abbr}{source_index}{pname} at z = "
+                                                      f"{rs.pos[2]:.5g} mm", **kwargs)
 
     # -- focus search (raytracer.py:1354-1640) ---------------------------------------------------------------
     focus_search_methods = ["RMS Spot Size", "Irradiance Variance", "Image Sharpness", "Image Center Sharpness"]
@@ -695,7 +707,7 @@ class Raytracer(Group):
             if i == iterations - 1:
                 rays_step += int(N - iterations*rays_step)
             begin, end = dist.shard_range(rays_step)
-            N_list = dist.broadcast_ints(split_rays(rays_step, powers), engine.device())
+            N_list = dist.shared_split(rays_step, powers, engine.device())
             self._trace_count += 1
             seed = (int(self.seed) << 20) + self._trace_count
             rays = self._generate(N_list, begin, end, seed)
@@ -706,10 +718,10 @@ class Raytracer(Group):
                 auto = [j for j in range(nd) if extentc[j] is None]
                 for g0 in range(0, len(auto), 8):
                     grp = auto[g0:g0 + 8]
-                    rng = engine.trace_render(scene, rays, [recs[j] for j in grp])
+                    rng = engine.trace_render(scene, rays, [recs[j] for j in grp], status=status_dev)
+                    rows = dist.gather_rows(rng.reshape(-1)).reshape(-1, len(grp), 4)    # (world, detectors, 4)
                     for k, j in enumerate(grp):
-                        dist.allreduce_range_(rng[k])
-                        r = rng[k].cpu().numpy()
+                        r = np.array([rows[:, k, 0].min(), rows[:, k, 1].max(), rows[:, k, 2].min(), rows[:, k, 3].max()])
                         e = self.detectors[detector_index[j]].pos[:2].repeat(2)
                         extentc[j] = r.copy() if r[0] <= r[1] else e
                 recs = det_records()
@@ -742,9 +754,9 @@ class Raytracer(Group):
             # messages are accumulated on the device: no host synchronisation per chunk, the next chunk's generation
             # and trace are queued while this one runs
             msgs_dev = msgs.clone() if msgs_dev is None else msgs_dev.add_(msgs)
-        dist.allreduce_sum_(msgs_dev)
-        msgs_cum += msgs_dev.cpu().numpy().astype(int)
-        engine.raise_status(int(status_dev.item()))
+        m, st = dist.reduce_msgs_status(msgs_dev, status_dev)
+        msgs_cum += m
+        engine.raise_status(st)
         for j in range(nd):
             dist.allreduce_sum_(images[j]._data_dev)
             dist.allreduce_sum_(images[j]._counts_dev)

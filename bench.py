@@ -220,7 +220,7 @@ def run_gpu(args):
         begin, end = dist.shard_range(N_total)
         RT._trace_count += 1
         seed = (int(RT.seed) << 20) + RT._trace_count
-        rays = RT._generate(N_list, begin, end, seed)
+        rays = RT._generated(scene, N_list, begin, end, seed)
         e0, e1 = ev(), ev()
         # the ray store (8.2 GB) is allocated once and overwritten every step: steady-state serving pattern
         if not stores:

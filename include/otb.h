@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OTB_ABI_VERSION 1
+#define OTB_ABI_VERSION 2
 
 typedef enum OtbStatus {
     OTB_OK = 0,
@@ -194,6 +194,7 @@ typedef struct OtbScene OtbScene;   /* opaque, device-resident copy of the descr
 
 /* ---- ray bundles -------------------------------------------------------------------------- */
 /* Initial rays = output of RaySource.create_rays (ray_source.py:204-437), SoA planes. */
+struct OtbGenerator;
 typedef struct OtbRays {
     int64_t N;
     const double* p0_d;    /* (N,3) F-order */
@@ -204,6 +205,10 @@ typedef struct OtbRays {
     const double* hurb_z_d; /* optional injected standard normals, shape (n_hurb, 2, N); NULL = Philox */
     uint64_t seed;         /* Philox key for HURB when hurb_z_d == NULL */
     int64_t ray_offset;    /* global id of local ray 0 (multi-GPU shards) */
+    const struct OtbGenerator* gen_h;  /* non-NULL: the N rays are GENERATED inside the trace kernel (fused
+                              RaySource.create_rays, see OtbGenerator below); p0_d .. wl_d are ignored and may be NULL.
+                              A bundle generated this way never exists in HBM: section 0 of the ray store receives
+                              its positions / weights / polarisation / wavelengths like any other section. */
 } OtbRays;
 
 /* Per-surface ray storage = RayStorage arrays (ray_storage.py:80-90). */
@@ -239,7 +244,9 @@ typedef enum OtbSourceShape {
     OTB_SHAPE_POINT = 0, OTB_SHAPE_LINE = 1, OTB_SHAPE_CIRCLE = 2, OTB_SHAPE_RING = 3,
     OTB_SHAPE_RECT = 4, OTB_SHAPE_IMAGE_RGB = 5, OTB_SHAPE_IMAGE_GRAY = 6
 } OtbSourceShape;
-typedef enum OtbOrientation { OTB_OR_CONSTANT = 0, OTB_OR_CONVERGING = 1 } OtbOrientation;
+typedef enum OtbOrientation { OTB_OR_CONSTANT = 0, OTB_OR_CONVERGING = 1,
+    OTB_OR_FUNCTION = 2   /* or_func(x, y) (ray_source.py:274-276) as a compiled device function */
+} OtbOrientation;
 typedef enum OtbDivergence {
     OTB_DIV_NONE = 0, OTB_DIV_LAMBERTIAN = 1, OTB_DIV_ISOTROPIC = 2, OTB_DIV_FUNCTION = 3
 } OtbDivergence;
@@ -283,7 +290,23 @@ typedef struct OtbSource {
     int32_t pix_cdf_off, pix_cdf_n;     /* image: pixel indices (pix_cdf_n doubles) then cumulative pixel power F */
     int32_t pix_rgb_off;                /* RGB image: primary thresholds (r, r+g) per pixel, 2 doubles each */
     int32_t srgb_off;                   /* RGB image: wl[5000], F_r[5000], F_g[5000], F_b[5000] (srgb.py:528-551) */
+    int32_t or_func_id;                 /* OTB_OR_FUNCTION: user device-function slot */
+    int32_t coherent;                   /* 1: warp-coherent bundle order.  The reference shuffles every stratified sample
+                                           (random.py:41-45); with this flag the strata of ONE random variable (the
+                                           direction inside the divergence cone, else the position on the source) are
+                                           handed out in blocks of 32 neighbouring cells, so the 32 rays of a warp meet
+                                           stops and lens edges together.  Same cells, same distribution of the bundle;
+                                           only the ORDER of the rays inside a source block is less random. */
 } OtbSource;
+
+/* On-device generation fused into otb_trace_store / otb_trace_render (OtbRays.gen_h): the same source records and
+ * tables otb_generate_rays takes.  sources_h[i].ray_start / n_rays tile [0, OtbRays.N). */
+typedef struct OtbGenerator {
+    const OtbSource* sources_h;
+    int32_t n_sources;
+    int32_t pad;
+    const double* gen_aux_d;
+} OtbGenerator;
 
 typedef struct OtbDeviceInfo {
     int32_t device, sm_major, sm_minor, sm_count;

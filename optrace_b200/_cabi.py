@@ -51,7 +51,7 @@ class OtbSceneDesc(C.Structure):
 class OtbRays(C.Structure):
     _fields_ = [("N", C.c_int64), ("p0_d", C.c_void_p), ("s0_d", C.c_void_p), ("pol0_d", C.c_void_p),
                 ("w0_d", C.c_void_p), ("wl_d", C.c_void_p), ("hurb_z_d", C.c_void_p),
-                ("seed", C.c_uint64), ("ray_offset", C.c_int64)]
+                ("seed", C.c_uint64), ("ray_offset", C.c_int64), ("gen_h", C.c_void_p)]
 
 
 class OtbRayStore(C.Structure):
@@ -77,7 +77,12 @@ class OtbSource(C.Structure):
                 ("wl_tab_off", C.c_int32), ("wl_tab_n", C.c_int32), ("div_tab_off", C.c_int32),
                 ("div_tab_n", C.c_int32), ("pol_tab_off", C.c_int32), ("pol_tab_n", C.c_int32),
                 ("pix_cdf_off", C.c_int32), ("pix_cdf_n", C.c_int32), ("pix_rgb_off", C.c_int32),
-                ("srgb_off", C.c_int32)]
+                ("srgb_off", C.c_int32), ("or_func_id", C.c_int32), ("coherent", C.c_int32)]
+
+
+class OtbGenerator(C.Structure):
+    _fields_ = [("sources_h", C.POINTER(OtbSource)), ("n_sources", C.c_int32), ("pad", C.c_int32),
+                ("gen_aux_d", C.c_void_p)]
 
 
 class OtbDeviceInfo(C.Structure):
@@ -155,7 +160,7 @@ def lib(path: os.PathLike | None = None) -> C.CDLL:
     for name, (res, args) in SYMBOLS.items():
         f = getattr(l, name)
         f.restype, f.argtypes = res, args
-    if l.otb_abi_version() != 1:
+    if l.otb_abi_version() != 2:
         raise EngineError("ABI version mismatch between _cabi.py and libotb.so")
     if path is None:
         _lib = l

@@ -212,7 +212,7 @@ int otb_trace_store(const OtbScene* scene, const OtbRays* rays, const OtbRayStor
                       (long long)out->N, out->nt, (long long)rays->N, scene->nt);
         return OTB_ERR_INVALID_ARG;
     }
-    if (!rays->p0_d || !rays->s0_d || !rays->w0_d || !rays->wl_d || (!scene->k.no_pol && !rays->pol0_d)
+    if ((!rays->gen_h && (!rays->p0_d || !rays->s0_d || !rays->w0_d || !rays->wl_d || (!scene->k.no_pol && !rays->pol0_d)))
         || !out->p_d || !out->s_d || !out->w_d || !out->n_d || !out->wl_d || (!scene->k.no_pol && !out->pol_d)) {
         otb_set_error("missing ray array");
         return OTB_ERR_INVALID_ARG;

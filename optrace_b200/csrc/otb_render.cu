@@ -9,6 +9,7 @@
 // binned hits are identical to those of the store path.
 #include <string.h>
 #include "otb_step.cuh"
+#include "otb_gen.cuh"
 #include "otb_bin.cuh"
 
 #define OTB_RENDER_THREADS 128
@@ -34,7 +35,10 @@ struct RenderArgs {
     unsigned long long* msgs;
     int* status;
     int nt;
+    int64_t k_begin, k_end;     // ray range of this launch
+    GenBlock G;                 // G.nsrc > 0: rays are generated here (otb_gen.cuh)
 };
+static_assert(sizeof(RenderArgs) <= 32764, "kernel parameter block exceeds the 32 KB limit");
 
 struct DetState {
     double X, Y;
@@ -140,11 +144,23 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
     double rg[OTB_MAX_DET][4];
     for (int d = 0; d < OTB_MAX_DET; ++d) { rg[d][0] = INFINITY; rg[d][1] = -INFINITY; rg[d][2] = INFINITY; rg[d][3] = -INFINITY; }
 
-    for (int64_t base = (int64_t)blockIdx.x*blockDim.x; base < N; base += (int64_t)gridDim.x*blockDim.x) {
+    const bool generate = a.G.nsrc > 0;
+    for (int64_t base = a.k_begin + (int64_t)blockIdx.x*blockDim.x; base < a.k_end; base += (int64_t)gridDim.x*blockDim.x) {
         const int64_t ray = base + threadIdx.x;
-        const bool valid = ray < N;
+        const bool valid = ray < a.k_end;
         RayState r;
-        if (valid) {
+        if (generate) {
+            GenRay gr;
+            generate_ray(a.G, valid ? ray : a.k_begin, gr);
+            if (valid && gr.neg_dir) atomicOr(a.status, OTB_STATUS_NEG_DIR);
+            r.p = gr.p;
+            r.s = gr.s;
+            r.w = valid ? gr.w : 0.0f;
+            r.wl = gr.wl;
+            r.pol[0] = POL ? gr.pol[0] : 0.0f;
+            r.pol[1] = POL ? gr.pol[1] : 0.0f;
+            r.pol[2] = POL ? gr.pol[2] : 0.0f;
+        } else if (valid) {
             r.p = v3(a.in.p0_d[ray], a.in.p0_d[ray + N], a.in.p0_d[ray + 2*N]);
             r.s = v3(a.in.s0_d[ray], a.in.s0_d[ray + N], a.in.s0_d[ray + 2*N]);
             r.w = a.in.w0_d[ray];
@@ -234,6 +250,9 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
         trace_render_kernel<POL, CAPS><<<blocks, OTB_RENDER_THREADS, smem, st>>>(a); } while (0)
 
 int otb_observer_table(const double** out);
+int otb_check_sources(const OtbSource* sources_h, int n_sources, int64_t N);
+void otb_fill_genblock(GenBlock* G, const OtbSource* sources_h, int g0, int nsrc, const double* gen_aux_d, uint64_t seed,
+                       int64_t ray_offset, int no_pol);
 BinGrid otb_make_grid(const double extent[4], int Nx, int Ny);
 int otb_sm_count();
 
@@ -284,10 +303,31 @@ extern "C" int otb_trace_render(const OtbScene* scene, const OtbRays* rays, int 
     a.status = status_d;
     a.nt = scene->nt;
     const int64_t N = rays->N;
-    int64_t blocks_needed = (N + OTB_RENDER_THREADS - 1)/OTB_RENDER_THREADS;
     size_t smem = sizeof(int)*OTB_NMSG*scene->nt;
     bool lean = scene->caps == OTB_CAPS_LENS;
     for (int d = 0; d < n_det; ++d) if (dets_h[d].surface.kind == OTB_SURF_TILTED) lean = false;
+    // ray ranges: one launch for an injected bundle, one per group of <= OTB_GEN_MAXSRC sources when generating
+    const OtbGenerator* gen = rays->gen_h;
+    if (gen) { if (int rc = otb_check_sources(gen->sources_h, gen->n_sources, N)) return rc; }
+    else if (!rays->p0_d || !rays->s0_d || !rays->w0_d || !rays->wl_d || (!scene->k.no_pol && !rays->pol0_d)) {
+        otb_set_error("missing ray array");
+        return OTB_ERR_INVALID_ARG;
+    }
+    const int n_groups = gen ? (gen->n_sources + OTB_GEN_MAXSRC - 1)/OTB_GEN_MAXSRC : 1;
+    for (int grp = 0; grp < n_groups; ++grp) {
+    if (gen) {
+        const int g0 = grp*OTB_GEN_MAXSRC;
+        const int nsrc = (gen->n_sources - g0 < OTB_GEN_MAXSRC) ? gen->n_sources - g0 : OTB_GEN_MAXSRC;
+        otb_fill_genblock(&a.G, gen->sources_h, g0, nsrc, gen->gen_aux_d, rays->seed, rays->ray_offset, scene->k.no_pol);
+        a.k_begin = gen->sources_h[g0].ray_start;
+        a.k_end = gen->sources_h[g0 + nsrc - 1].ray_start + gen->sources_h[g0 + nsrc - 1].n_rays;
+        if (a.k_end <= a.k_begin) continue;
+    } else {
+        a.G.nsrc = 0;
+        a.k_begin = 0;
+        a.k_end = N;
+    }
+    const int64_t blocks_needed = (a.k_end - a.k_begin + OTB_RENDER_THREADS - 1)/OTB_RENDER_THREADS;
 #if OTB_SPEC
     if (!otb_scene_equal(scene->k, K_SPEC_HOST)) {
         otb_set_error("this engine build is specialised for a different scene");
@@ -306,5 +346,6 @@ extern "C" int otb_trace_render(const OtbScene* scene, const OtbRays* rays, int 
 #endif
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return otb_cuda_fail(e, "trace_render_kernel launch");
+    }
     return OTB_OK;
 }

@@ -248,6 +248,21 @@ template <bool POL, int CAPS>
 __device__ __forceinline__ void trace_step(const KScene& sc, const double* __restrict__ aux, const OtbStep& st, RayState& r,
                                            StepFlags& fl, double za, double zb, int* status)
 {
+    // A warp whose 32 rays are all absorbed (w == 0) has nothing to intersect or refract: dead rays repeat their
+    // position, polarisation and zero weight in every later section (raytracer.py:309-312) and only follow the media
+    // (n_list is written for every ray, raytracer.py:343, 362).  Coherent bundles (OtbSource.coherent) make such
+    // warps the rule behind a stop instead of the exception.
+    if (!__any_sync(0xffffffffu, r.w > 0.0f)) {
+        fl.ill = fl.absorb_missing = fl.tir = fl.outline = fl.hurb_neg = false;
+        if (st.role <= OTB_STEP_IDEAL_LENS) {
+            const double n2 = medium_n(sc.media[st.medium_after], aux, (double)r.wl);
+            if (n2 < 1.0) atomicOr(status, OTB_STATUS_NBELOW1);
+            r.n = n2;
+        } else if (CAPS == OTB_CAPS_FULL && st.role == OTB_STEP_APERTURE && st.hurb) {
+            fl.hurb_neg = r.s.z < 0;          // booked for every ray, alive or not (raytracer.py:484-486)
+        }
+        return;
+    }
 #ifndef OTB_NO_FAST_PATH
     const KSurface& S = sc.surf[st.surface];
     bool done = false;

@@ -4,8 +4,10 @@
 //
 // The scene (steps, surfaces, media, filters) is a __grid_constant__ kernel parameter: warp-uniform values come
 // from the constant bank, not from global memory.
-// HBM traffic per ray: read 68 B (injected bundle) ; write nt*48 + 24 B (pol) or nt*36 + 24 B (no_pol).
+// HBM traffic per ray: write nt*48 + 28 B (pol) or nt*36 + 28 B (no_pol); read 68 B only for INJECTED bundles —
+// with OtbRays.gen_h the kernel draws its rays itself (generate_ray, otb_gen.cuh) and the bundle never exists in HBM.
 #include "otb_step.cuh"
+#include "otb_gen.cuh"
 
 #define OTB_TRACE_THREADS 128
 #ifndef OTB_TRACE_MINBLOCKS
@@ -18,7 +20,10 @@ struct TraceArgs {
     OtbRayStore out;
     unsigned long long* msgs;   // [OTB_NMSG * nt]
     int* status;
+    int64_t k_begin, k_end;     // ray range of this launch (more than OTB_GEN_MAXSRC sources: one launch per group)
+    GenBlock G;                 // G.nsrc > 0: rays are generated here
 };
+static_assert(sizeof(TraceArgs) <= 32764, "kernel parameter block exceeds the 32 KB limit");
 
 #ifndef OTB_STEP_UNROLL
 #define OTB_STEP_UNROLL 1
@@ -97,21 +102,37 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
 
     const int64_t Nnt = N*(int64_t)nt;
 
-    for (int64_t base = (int64_t)blockIdx.x*blockDim.x; base < N; base += (int64_t)gridDim.x*blockDim.x) {
+    const bool generate = a.G.nsrc > 0;
+    for (int64_t base = a.k_begin + (int64_t)blockIdx.x*blockDim.x; base < a.k_end; base += (int64_t)gridDim.x*blockDim.x) {
         const int64_t ray = base + threadIdx.x;
-        const bool valid = ray < N;
-        const int64_t rr = valid ? ray : 0;          // clamp so that every lane addresses valid memory
+        const bool valid = ray < a.k_end;
+        const int64_t rr = valid ? ray : a.k_begin;  // clamp so that every lane addresses valid memory
         RayState r;
-        r.p = v3(a.in.p0_d[rr], a.in.p0_d[rr + N], a.in.p0_d[rr + 2*N]);
-        r.s = v3(a.in.s0_d[rr], a.in.s0_d[rr + N], a.in.s0_d[rr + 2*N]);
-        r.w = valid ? a.in.w0_d[rr] : 0.0f;
-        r.wl = a.in.wl_d[rr];
-        if (POL) {
-            r.pol[0] = a.in.pol0_d[rr];
-            r.pol[1] = a.in.pol0_d[rr + N];
-            r.pol[2] = a.in.pol0_d[rr + 2*N];
+        if (generate) {
+            // fused RaySource.create_rays: the ray is drawn here (Philox counter = global ray id) instead of being
+            // written by a generator kernel and read back
+            GenRay gr;
+            generate_ray(a.G, rr, gr);
+            if (valid && gr.neg_dir) atomicOr(a.status, OTB_STATUS_NEG_DIR);
+            r.p = gr.p;
+            r.s = gr.s;
+            r.w = valid ? gr.w : 0.0f;
+            r.wl = gr.wl;
+            r.pol[0] = POL ? gr.pol[0] : 0.0f;
+            r.pol[1] = POL ? gr.pol[1] : 0.0f;
+            r.pol[2] = POL ? gr.pol[2] : 0.0f;
         } else {
-            r.pol[0] = r.pol[1] = r.pol[2] = 0.0f;
+            r.p = v3(a.in.p0_d[rr], a.in.p0_d[rr + N], a.in.p0_d[rr + 2*N]);
+            r.s = v3(a.in.s0_d[rr], a.in.s0_d[rr + N], a.in.s0_d[rr + 2*N]);
+            r.w = valid ? a.in.w0_d[rr] : 0.0f;
+            r.wl = a.in.wl_d[rr];
+            if (POL) {
+                r.pol[0] = a.in.pol0_d[rr];
+                r.pol[1] = a.in.pol0_d[rr + N];
+                r.pol[2] = a.in.pol0_d[rr + 2*N];
+            } else {
+                r.pol[0] = r.pol[1] = r.pol[2] = 0.0f;
+            }
         }
         r.n = medium_n(sc.media[sc.medium0], aux, (double)r.wl);
         if (valid && r.n < 1.0) atomicOr(a.status, OTB_STATUS_NBELOW1);
@@ -164,6 +185,12 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
         if (smsgs[i]) atomicAdd(&a.msgs[i], (unsigned long long)smsgs[i]);
 }
 
+int otb_check_sources(const OtbSource* sources_h, int n_sources, int64_t N);
+void otb_fill_genblock(GenBlock* G, const OtbSource* sources_h, int g0, int nsrc, const double* gen_aux_d, uint64_t seed,
+                       int64_t ray_offset, int no_pol);
+
+static int launch_trace_store_range(const OtbScene* scene, TraceArgs& a, cudaStream_t stream, int sm_count);
+
 int otb_launch_trace_store(const OtbScene* scene, const OtbRays* rays, const OtbRayStore* out,
                            int64_t* msgs_d, int32_t* status_d, cudaStream_t stream, int sm_count)
 {
@@ -175,9 +202,30 @@ int otb_launch_trace_store(const OtbScene* scene, const OtbRays* rays, const Otb
     a.status = status_d;
     const int64_t N = out->N;
     if (N <= 0) return OTB_OK;
+    if (!rays->gen_h) {
+        a.G.nsrc = 0;
+        a.k_begin = 0;
+        a.k_end = N;
+        return launch_trace_store_range(scene, a, stream, sm_count);
+    }
+    const OtbGenerator& gen = *rays->gen_h;
+    if (int rc = otb_check_sources(gen.sources_h, gen.n_sources, N)) return rc;
+    for (int g0 = 0; g0 < gen.n_sources; g0 += OTB_GEN_MAXSRC) {
+        const int nsrc = (gen.n_sources - g0 < OTB_GEN_MAXSRC) ? gen.n_sources - g0 : OTB_GEN_MAXSRC;
+        otb_fill_genblock(&a.G, gen.sources_h, g0, nsrc, gen.gen_aux_d, rays->seed, rays->ray_offset, scene->k.no_pol);
+        a.k_begin = gen.sources_h[g0].ray_start;
+        a.k_end = gen.sources_h[g0 + nsrc - 1].ray_start + gen.sources_h[g0 + nsrc - 1].n_rays;
+        if (a.k_end <= a.k_begin) continue;
+        if (int rc = launch_trace_store_range(scene, a, stream, sm_count)) return rc;
+    }
+    return OTB_OK;
+}
+
+static int launch_trace_store_range(const OtbScene* scene, TraceArgs& a, cudaStream_t stream, int sm_count)
+{
     const int threads = OTB_TRACE_THREADS;
-    int64_t blocks_needed = (N + threads - 1)/threads;
-    size_t smem = sizeof(int)*OTB_NMSG*out->nt;
+    int64_t blocks_needed = (a.k_end - a.k_begin + threads - 1)/threads;
+    size_t smem = sizeof(int)*OTB_NMSG*a.out.nt;
 #define OTB_LAUNCH_STORE(POL, CAPS) do { \
         int blocks = otb_one_wave_grid(trace_store_kernel<POL, CAPS>, threads, smem, sm_count, blocks_needed); \
         trace_store_kernel<POL, CAPS><<<blocks, threads, smem, stream>>>(a); } while (0)

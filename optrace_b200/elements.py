@@ -328,10 +328,11 @@ class RaySource(Element):
             rec["geom"][4] = 1.0 if sf._angle else 0.0
         rec["pos"] = [float(v) for v in sf.pos]
 
-        if self.orientation == "Function":
-            raise NotImplementedError("orientation='Function' (Python or_func per ray) is not supported by the "
-                                      "device generator; pass pre-generated rays instead.")
-        rec["orientation"] = 0 if self.orientation == "Constant" else 1
+        if self.orientation == "Function" and not callable(self.or_func):
+            raise TypeError("RaySource.or_func needs to be callable.")
+        # "Function": or_func(x, y) is translated into a device function (userfunc.py, kind "orient"); the scene
+        # flattening registers it and fills in the slot (scene.flatten_raytracer)
+        rec["orientation"] = ["Constant", "Converging", "Function"].index(self.orientation)
         rec["s"] = [float(v) for v in self.s]
         rec["conv_pos"] = [float(v) for v in self.conv_pos]
 

@@ -183,12 +183,25 @@ class DeviceRays:
                           None if hurb_z is None else _torch().from_numpy(
                               np.ascontiguousarray(hurb_z, dtype=np.float64).ravel()).to(device()), seed)
 
+    @staticmethod
+    def generated(N, sources, n_sources, aux_d, seed, ray_offset):
+        """bundle that exists only as a description: the trace kernels draw the rays themselves (OtbRays.gen_h)"""
+        r = DeviceRays(N, None, None, None, None, None, None, seed, ray_offset)
+        g = _cabi.OtbGenerator()
+        g.sources_h = C.cast(sources, C.POINTER(_cabi.OtbSource))
+        g.n_sources = n_sources
+        g.gen_aux_d = aux_d.data_ptr()
+        r._gen = (g, sources, aux_d)         # keeps the ctypes records and the table buffer alive
+        return r
+
     def c_struct(self):
         r = _cabi.OtbRays()
         r.N = self.N
         r.p0_d, r.s0_d, r.pol0_d = dptr(self.p0), dptr(self.s0), dptr(self.pol0)
         r.w0_d, r.wl_d, r.hurb_z_d = dptr(self.w0), dptr(self.wl), dptr(self.hurb_z)
         r.seed, r.ray_offset = self.seed, self.ray_offset
+        gen = getattr(self, "_gen", None)
+        r.gen_h = C.cast(C.pointer(gen[0]), C.c_void_p) if gen is not None else None
         return r
 
 

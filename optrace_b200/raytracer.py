@@ -36,10 +36,6 @@ class Raytracer(Group):
     """re-send scene and sampling tables host -> device on every trace even when unchanged (used by bench.py's
     end-to-end measurement, whose timed region must contain the host -> device copy of the step's inputs)"""
     use_specialised_kernels: bool = True
-    overlap_generation: bool = False
-    """generate the bundle of a trace on a side stream, beside detector kernels still queued on the compute stream.
-    Off by default: on one GPU it gains ~0.1 ms per 10 M rays, on several GPUs it moves the image all-reduce of the
-    previous call from the generator's shadow onto the trace kernel (2 x B200: 5.5 instead of 3.9 ms per trace)."""
     arithmetic: str = "exact"
     """floating-point contract of the lens-surface step on the device.  "exact" (default): every + - * / sqrt rounds
     like the reference's numpy float64 operation, results are bit-identical to the reference on closed-form
@@ -109,7 +105,8 @@ class Raytracer(Group):
         so that in-place edits of a `pos` array are still noticed."""
         quick = (_state.EPOCH[0], len(self.elements), tuple(self.outline), self.no_pol, self.use_hurb, self.HURB_FACTOR,
                  self.arithmetic,
-                 id(self.n0), tuple((id(el), el._front.pos.tobytes()) for el in self.elements))
+                 id(self.n0), tuple((id(el), el._front.pos.tobytes()) for el in self.elements),
+                 tuple((id(rs), id(rs.or_func)) for rs in self.ray_sources if rs.orientation == "Function"))
         cache = self.__dict__.get("_geom_cache")
         if cache is not None and cache[0] == quick:
             return cache[1]
@@ -117,7 +114,8 @@ class Raytracer(Group):
                      state_of(getattr(el, "n", None)), state_of(getattr(el, "n2", None)),
                      state_of(getattr(el, "spectrum", None)), getattr(el, "D", None))
                     for el in self.elements if isinstance(el, (Lens, Filter, Aperture)))
-        key = (els, tuple(self.outline), state_of(self.n0), self.no_pol, self.use_hurb, self.HURB_FACTOR, self.arithmetic)
+        key = (els, tuple(self.outline), state_of(self.n0), self.no_pol, self.use_hurb, self.HURB_FACTOR, self.arithmetic,
+               quick[-1])
         object.__setattr__(self, "_geom_cache", (quick, key))
         return key
 
@@ -296,18 +294,21 @@ class Raytracer(Group):
         self._gen_cache = (key, recs, aux_d, aux_h)
         return recs, aux_d
 
-    def _generate(self, N_list, begin: int, end: int, seed: int):
-        """otb_generate_rays for the local shard [begin, end) of the global ray range"""
-        torch = engine._torch()
-        lib = engine.ensure_init()
-        main = torch.cuda.current_stream()
-        gs = engine.gen_stream() if self.overlap_generation else main
-        with torch.cuda.stream(gs):
-            recs, aux_d = self._generator_tables()          # (re-)upload of the sampling tables on the same stream
+    coherent_bundles: bool = True
+    """order of the rays inside a generated bundle.  The reference shuffles every stratified sample (random.py:41-45);
+    with this flag (default) the strata of ONE random variable — the direction inside the divergence cone when the
+    source has one, else the position on the source area — are handed out in blocks of 32 neighbouring cells, so the
+    32 rays of a warp meet stops and lens edges together and warps whose rays are all absorbed skip the surface
+    arithmetic.  Same cells, same distributions, same images; only the order of the rays within a source block is
+    less random (a slice rays[:k] is a set of 32-ray clusters instead of a uniform subsample).  False = full shuffle."""
+
+    def _source_records(self, scene, N_list, begin: int, end: int):
+        """OtbSource array of the local shard [begin, end) of the global ray range + the table buffer on the device"""
+        recs, aux_d = self._generator_tables()          # (re-)upload of the sampling tables on the current stream
         B_list = np.concatenate(([0], np.cumsum(N_list)))
         sl = dist.source_slices(B_list, begin, end)
-        n = end - begin
         arr = (_cabi.OtbSource*max(len(sl), 1))()
+        fids = scene.flat.source_func_ids
         for k, (i, start, cnt) in enumerate(sl):
             r, S = recs[i], arr[k]
             S.shape, S.orientation, S.divergence = r["shape"], r["orientation"], r["divergence"]
@@ -324,29 +325,46 @@ class Raytracer(Group):
             for f in ("wl_tab_off", "wl_tab_n", "div_tab_off", "div_tab_n", "pol_tab_off", "pol_tab_n",
                       "pix_cdf_off", "pix_cdf_n", "pix_rgb_off", "srgb_off"):
                 setattr(S, f, int(r[f]))
+            S.or_func_id = fids.get(id(self.ray_sources[i]), -1)
+            S.coherent = int(bool(self.coherent_bundles))
+        return arr, len(sl), aux_d
+
+    def _generate(self, N_list, begin: int, end: int, seed: int, scene=None):
+        """otb_generate_rays for the local shard [begin, end) of the global ray range: the stand-alone generator
+        (tests, tools, injected-bundle workflows).  trace() and iterative_render() do not call it: they hand the
+        source records to the trace kernels, which draw the rays themselves (engine.DeviceRays.generated)."""
+        torch = engine._torch()
+        engine.ensure_init()
+        scene = scene or self._scene_handle()
+        lib = scene.lib
+        n = end - begin
+        arr, ns, aux_d = self._source_records(scene, N_list, begin, end)
         d = engine.device()
-        # The generator runs on its own stream: the bundle does not depend on kernels of a previous
-        # detector_image() that may still be queued on the compute stream (render: latency-bound, generator:
-        # ALU-bound, they share the SMs well).  The compute stream waits for it before the trace kernel.
-        with torch.cuda.stream(gs):
-            p0 = torch.empty(3*n, dtype=torch.float64, device=d)
-            s0 = torch.empty(3*n, dtype=torch.float64, device=d)
-            pol0 = None if self.no_pol else torch.empty(3*n, dtype=torch.float32, device=d)
-            w0 = torch.empty(n, dtype=torch.float32, device=d)
-            wl = torch.empty(n, dtype=torch.float32, device=d)
-            status = torch.zeros(1, dtype=torch.int32, device=d)
-            _cabi.check(lib.otb_generate_rays(arr, len(sl), engine.dptr(aux_d), n, seed, begin, int(self.no_pol),
-                                              engine.dptr(p0), engine.dptr(s0), engine.dptr(pol0), engine.dptr(w0),
-                                              engine.dptr(wl), engine.dptr(status),
-                                              C.c_void_p(gs.cuda_stream)), lib)
-        if gs is not main:
-            main.wait_stream(gs)
-            for t in (p0, s0, pol0, w0, wl, status):
-                if t is not None:
-                    t.record_stream(main)       # consumed by the trace on the compute stream
+        p0 = torch.empty(3*n, dtype=torch.float64, device=d)
+        s0 = torch.empty(3*n, dtype=torch.float64, device=d)
+        pol0 = None if self.no_pol else torch.empty(3*n, dtype=torch.float32, device=d)
+        w0 = torch.empty(n, dtype=torch.float32, device=d)
+        wl = torch.empty(n, dtype=torch.float32, device=d)
+        status = torch.zeros(1, dtype=torch.int32, device=d)
+        _cabi.check(lib.otb_generate_rays(arr, ns, engine.dptr(aux_d), n, seed, begin, int(self.no_pol),
+                                          engine.dptr(p0), engine.dptr(s0), engine.dptr(pol0), engine.dptr(w0),
+                                          engine.dptr(wl), engine.dptr(status), engine.stream_ptr()), lib)
         rays = engine.DeviceRays(n, p0, s0, pol0, w0, wl, None, seed, begin)
         rays.gen_status = status        # checked when the trace result is synchronised anyway
         return rays
+
+    fused_generation: bool = False
+    """draw the rays inside the trace kernels (OtbRays.gen_h) instead of with the generator kernel.  A fused bundle
+    never exists in HBM (68 B per ray less memory and traffic, identical rays bit for bit), but the trace kernels run
+    at 16 warps per SM and the generator's integer work does not hide behind their fp64 chains: measured on the
+    double-Gauss workload 4.53 ms fused against 3.67 + 0.66 ms separate.  Worth it when device memory is the limit."""
+
+    def _generated(self, scene, N_list, begin: int, end: int, seed: int):
+        """the bundle of a trace: generated by the generator kernel (default) or described for the fused path"""
+        if not self.fused_generation:
+            return self._generate(N_list, begin, end, seed, scene)
+        arr, ns, aux_d = self._source_records(scene, N_list, begin, end)
+        return engine.DeviceRays.generated(end - begin, arr, ns, aux_d, seed, begin)
 
     # -- trace -----------------------------------------------------------------------------------------
     def trace(self, N: int) -> None:
@@ -367,7 +385,7 @@ class Raytracer(Group):
                     "Change the power ratio or raise the overall ray number")
         self._trace_count += 1
         seed = (int(self.seed) << 20) + self._trace_count
-        rays = self._generate(N_list, begin, end, seed)
+        rays = self._generated(scene, N_list, begin, end, seed)
         self._run_trace(scene, rays, N_list, N, begin)
 
     def trace_rays(self, p, s, pol, w, wl, hurb_z=None, N_list=None) -> None:
@@ -710,8 +728,9 @@ class Raytracer(Group):
             N_list = dist.shared_split(rays_step, powers, engine.device())
             self._trace_count += 1
             seed = (int(self.seed) << 20) + self._trace_count
-            rays = self._generate(N_list, begin, end, seed)
-            status_dev.bitwise_or_(rays.gen_status)
+            rays = self._generated(scene, N_list, begin, end, seed)
+            if getattr(rays, "gen_status", None) is not None:
+                status_dev.bitwise_or_(rays.gen_status)
             recs = det_records()
             if i == 0:
                 # auto extents from the first chunk (raytracer.py:1042-1046, 1262): range pass without binning

@@ -37,6 +37,7 @@ class FlatScene:
         self.n_hurb = 0
         self.hurb_factor = 2**0.5
         self.user_funcs: list = []      # (kind, callable, args) for the device-function transpiler
+        self.source_func_ids: dict = {}  # id(RaySource) -> slot of its orientation function
         self._keep = None
 
     @property
@@ -119,7 +120,7 @@ class FlatScene:
             F[i].c[:] = r["c"]
         aux = np.ascontiguousarray(self.aux if self.aux.shape[0] else np.zeros(1), dtype=np.float64)
         d = _cabi.OtbSceneDesc()
-        d.abi_version = 1
+        d.abi_version = 2
         d.n_surfaces, d.n_steps, d.n_media, d.n_filters = ns, nst, nm, nf
         d.no_pol, d.medium0, d.n_hurb, d.n_aux = int(self.no_pol), self.medium0, self.n_hurb, self.aux.shape[0]
         d.outline[:] = self.outline
@@ -202,6 +203,12 @@ def flatten_raytracer(rt) -> FlatScene:
             if bend and not isinstance(el.surface, (RingSurface, SlitSurface)):
                 raise ValueError(f"Ray bending for surface type {type(el.surface).__name__} not implemented.")
             step(ROLE_APERTURE, el.surface, hurb=int(bend))
+    # orientation functions of the sources (ray_source.py:274-276) are compiled into the same engine variant as the
+    # scene's surface / medium callables: the generator runs inside the trace kernels
+    fs.source_func_ids = {}
+    for rs in getattr(rt, "ray_sources", []):
+        if getattr(rs, "orientation", None) == "Function" and callable(rs.or_func):
+            fs.source_func_ids[id(rs)] = fs._add_func("orient", rs.or_func, dict(rs.or_args))
     return fs
 
 

@@ -53,6 +53,9 @@ class _Emitter:
     def __init__(self, fn, params, kwargs):
         self.fn, self.params, self.kwargs = fn, params, dict(kwargs)
         self.locals = set()
+        self.vec_locals = {}        # name -> (c0, c1, c2): locals holding an (N, 3) array (orientation functions)
+        self.pre = []               # statements to emit before the expression under construction (vector temporaries)
+        self.ntmp = 0
         cv = inspect.getclosurevars(fn)
         self.env = {**cv.globals, **cv.nonlocals}
 
@@ -141,11 +144,121 @@ class _Emitter:
             return f"(({' && '.join(parts)}) ? 1.0 : 0.0)"
         if isinstance(node, ast.IfExp):
             return f"((({self.expr(node.test)}) != 0.0) ? {self.expr(node.body)} : {self.expr(node.orelse)})"
+        if isinstance(node, ast.Subscript):
+            k = self._component_index(node)
+            if k is not None:                       # v[:, k] / v[..., k] of an (N, 3) value
+                v = self.vec(node.value)
+                if v is None:
+                    self.fail(node, "component subscript of a non-vector value")
+                return v[k]
+            if self._is_newaxis(node):              # x[:, None] / x[:, np.newaxis]: broadcasting helper, same scalar
+                return self.expr(node.value)
+            self.fail(node, "subscript")
         if isinstance(node, ast.Call):
             return self.call(node)
         self.fail(node, type(node).__name__)
 
+    # ---- (N, 3) array values of orientation functions: per ray a 3-vector ------------------------------------
+    def _is_none_like(self, n) -> bool:
+        return (isinstance(n, ast.Constant) and n.value is None) or self.module_attr(n) == "newaxis"
+
+    def _is_full_slice(self, n) -> bool:
+        return (isinstance(n, ast.Slice) and n.lower is None and n.upper is None and n.step is None) or \
+            (isinstance(n, ast.Constant) and n.value is Ellipsis)
+
+    def _component_index(self, node):
+        sl = node.slice
+        if isinstance(sl, ast.Tuple) and len(sl.elts) == 2 and self._is_full_slice(sl.elts[0]) \
+                and isinstance(sl.elts[1], ast.Constant) and isinstance(sl.elts[1].value, int) and not isinstance(sl.elts[1].value, bool):
+            k = sl.elts[1].value
+            return k % 3 if -3 <= k < 3 else None
+        return None
+
+    def _is_newaxis(self, node) -> bool:
+        sl = node.slice
+        return isinstance(sl, ast.Tuple) and len(sl.elts) == 2 and self._is_full_slice(sl.elts[0]) and self._is_none_like(sl.elts[1])
+
+    def _tmp(self, value: str) -> str:
+        self.ntmp += 1
+        nm = f"otb_t{self.ntmp}"
+        self.pre.append(f"    const double {nm} = {value};")
+        return nm
+
+    def _three(self, node):
+        """the three element expressions of a tuple / list literal, else None"""
+        if isinstance(node, (ast.Tuple, ast.List)) and len(node.elts) == 3:
+            return tuple(self._tmp(self.expr(e)) for e in node.elts)
+        return None
+
+    def vec(self, node):
+        """(c0, c1, c2) C expressions when `node` evaluates to an (N, 3) array, else None"""
+        if isinstance(node, ast.Name):
+            return self.vec_locals.get(node.id)
+        if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
+            v = self.vec(node.operand)
+            if v is None:
+                return None
+            return tuple(f"(-{c})" for c in v) if isinstance(node.op, ast.USub) else v
+        if isinstance(node, ast.Attribute) and node.attr == "T":            # np.array([a, b, c]).T / np.vstack(...).T
+            inner = node.value
+            if isinstance(inner, ast.Call) and self.module_attr(inner.func) in ("array", "asarray", "vstack", "stack") \
+                    and inner.args and not inner.keywords:
+                return self._three(inner.args[0])
+            return None
+        if isinstance(node, ast.Call):
+            name = self.module_attr(node.func)
+            fname = node.func.attr if isinstance(node.func, ast.Attribute) else (node.func.id if isinstance(node.func, ast.Name) else None)
+            if name == "column_stack" and len(node.args) == 1:
+                return self._three(node.args[0])
+            if name == "stack" and len(node.args) >= 1:
+                ax = node.args[1] if len(node.args) > 1 else next((k.value for k in node.keywords if k.arg == "axis"), None)
+                if isinstance(ax, ast.UnaryOp) and isinstance(ax.op, ast.USub) and isinstance(ax.operand, ast.Constant):
+                    axv = -ax.operand.value
+                else:
+                    axv = ax.value if isinstance(ax, ast.Constant) else None
+                if axv in (1, -1):
+                    return self._three(node.args[0])
+                return None
+            if name == "transpose" and len(node.args) == 1 and isinstance(node.args[0], ast.Call) \
+                    and self.module_attr(node.args[0].func) in ("array", "asarray", "vstack"):
+                return self._three(node.args[0].args[0])
+            if fname == "normalize" and len(node.args) == 1:               # misc.normalize (misc.py:136-150)
+                v = self.vec(node.args[0])
+                if v is None:
+                    return None
+                l = self._tmp(f"sqrt((({v[0]}*{v[0]}) + ({v[1]}*{v[1]})) + ({v[2]}*{v[2]}))")
+                return tuple(self._tmp(f"({c}/{l})") for c in v)
+            if name == "where" and len(node.args) == 3:
+                a, b = self.vec(node.args[1]), self.vec(node.args[2])
+                if a is None and b is None:
+                    return None
+                c = self.expr(node.args[0])
+                a = a or (self.expr(node.args[1]),)*3
+                b = b or (self.expr(node.args[2]),)*3
+                return tuple(f"((({c}) != 0.0) ? {x} : {y})" for x, y in zip(a, b))
+            return None
+        if isinstance(node, ast.BinOp):
+            a, b = self.vec(node.left), self.vec(node.right)
+            if a is None and b is None:
+                return None
+            sym = {ast.Add: "+", ast.Sub: "-", ast.Mult: "*", ast.Div: "/"}.get(type(node.op))
+            if sym is None:
+                self.fail(node, f"operator {type(node.op).__name__} on an (N, 3) value")
+            if a is None:
+                sa = self._tmp(self.expr(node.left))
+                a = (sa, sa, sa)
+            if b is None:
+                sb = self._tmp(self.expr(node.right))
+                b = (sb, sb, sb)
+            return tuple(f"({x} {sym} {y})" for x, y in zip(a, b))
+        return None
+
     def call(self, node) -> str:
+        # np.linalg.norm(v, axis=1) of an (N, 3) value
+        if isinstance(node.func, ast.Attribute) and node.func.attr == "norm" and node.args:
+            v = self.vec(node.args[0])
+            if v is not None:
+                return f"sqrt((({v[0]}*{v[0]}) + ({v[1]}*{v[1]})) + ({v[2]}*{v[2]}))"
         name = self.module_attr(node.func)
         if name is None and isinstance(node.func, ast.Name) and node.func.id in ("abs", "float", "min", "max", "pow"):
             name = {"abs": "abs", "float": "float64", "min": "minimum", "max": "maximum", "pow": "power"}[node.func.id]
@@ -231,14 +344,31 @@ def translate(kind: str, fn, kwargs: dict, cname: str) -> str:
     em = _Emitter(fn, params, kw)
     lines = []
     ret = None
+    def flush():
+        lines.extend(em.pre)
+        em.pre.clear()
+
     for stmt in body:
         if isinstance(stmt, ast.Expr) and isinstance(stmt.value, ast.Constant) and isinstance(stmt.value.value, str):
             continue   # docstring
         if isinstance(stmt, ast.Assign) and len(stmt.targets) == 1 and isinstance(stmt.targets[0], ast.Name):
             nm = stmt.targets[0].id
+            v = em.vec(stmt.value) if kind == "orient" else None
+            if v is not None:                   # local holding an (N, 3) array
+                flush()
+                em.ntmp += 1
+                names = tuple(f"{nm}_{em.ntmp}_{c}" for c in "xyz")
+                for n_, c_ in zip(names, v):
+                    lines.append(f"    const double {n_} = {c_};")
+                em.vec_locals[nm] = names
+                em.locals.discard(nm)
+                continue
+            val = em.expr(stmt.value)
+            flush()
             decl = "" if nm in em.locals or nm in params else "double "
-            lines.append(f"    {decl}{nm} = {em.expr(stmt.value)};")
+            lines.append(f"    {decl}{nm} = {val};")
             em.locals.add(nm)
+            em.vec_locals.pop(nm, None)
         elif isinstance(stmt, ast.Return):
             ret = stmt.value
             break
@@ -247,14 +377,28 @@ def translate(kind: str, fn, kwargs: dict, cname: str) -> str:
     if ret is None:
         raise NotImplementedError(f"user callable {fn} has no return statement")
     args = ", ".join(f"double {p}" for p in params)
+    if kind == "orient":
+        v = em.vec(ret)
+        if v is None:
+            raise NotImplementedError(f"orientation function {fn}: the return value must be an (N, 3) array expression "
+                                      "(np.column_stack / np.stack(axis=1) / np.array([...]).T, optionally normalised)")
+        flush()
+        for c_, o_ in zip(v, ("otb_x", "otb_y", "otb_z")):
+            lines.append(f"    *{o_} = {c_};")
+        return (f"__device__ __forceinline__ void {cname}({args}, double* otb_x, double* otb_y, double* otb_z)\n{{\n"
+                + "\n".join(lines) + "\n}\n")
     if kind == "deriv2d":
         if not isinstance(ret, ast.Tuple) or len(ret.elts) != 2:
             raise NotImplementedError("a 2-D derivative function must return a tuple (dz/dx, dz/dy)")
-        lines.append(f"    *otb_dx = {em.expr(ret.elts[0])};")
-        lines.append(f"    *otb_dy = {em.expr(ret.elts[1])};")
+        dxv, dyv = em.expr(ret.elts[0]), em.expr(ret.elts[1])
+        flush()
+        lines.append(f"    *otb_dx = {dxv};")
+        lines.append(f"    *otb_dy = {dyv};")
         return (f"__device__ __forceinline__ void {cname}({args}, double* otb_dx, double* otb_dy)\n{{\n"
                 + "\n".join(lines) + "\n}\n")
-    lines.append(f"    return {em.expr(ret)};")
+    rv = em.expr(ret)
+    flush()
+    lines.append(f"    return {rv};")
     return f"__device__ __forceinline__ double {cname}({args})\n{{\n" + "\n".join(lines) + "\n}\n"
 
 
@@ -266,11 +410,12 @@ def generate_header(user_funcs) -> str:
            "__device__ __forceinline__ double otb_sign(double v) { return (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : v); }",
            "__device__ __forceinline__ double otb_pymod(double a, double b) { double r = fmod(a, b); "
            "return (r != 0.0 && ((r < 0.0) != (b < 0.0))) ? r + b : r; }", ""]
-    f1, f2, d2 = [], [], []
+    f1, f2, d2, v3 = [], [], [], []
     for i, (kind, fn, kwargs) in enumerate(user_funcs):
         out.append(f"// id {i}: {kind} {getattr(fn, '__qualname__', fn)} {kwargs}")
         out.append(translate(kind, fn, kwargs, f"otb_uf_{i}"))
-        (d2 if kind == "deriv2d" else (f1 if kind in ("surf1d", "mask1d", "deriv1d", "wl") else f2)).append(i)
+        (v3 if kind == "orient" else d2 if kind == "deriv2d" else
+         (f1 if kind in ("surf1d", "mask1d", "deriv1d", "wl") else f2)).append(i)
     out.append("__device__ __forceinline__ double otb_user_f1(int id, double a)\n{\n    switch (id) {")
     out += [f"    case {i}: return otb_uf_{i}(a);" for i in f1]
     out.append('    default: return nan("");\n    }\n}\n')
@@ -280,6 +425,9 @@ def generate_header(user_funcs) -> str:
     out.append("__device__ __forceinline__ void otb_user_d2(int id, double a, double b, double* dx, double* dy)\n{\n    switch (id) {")
     out += [f"    case {i}: otb_uf_{i}(a, b, dx, dy); break;" for i in d2]
     out.append('    default: *dx = nan(""); *dy = nan(""); break;\n    }\n}\n')
+    out.append("__device__ __forceinline__ void otb_user_v3(int id, double a, double b, double* x, double* y, double* z)\n{\n    switch (id) {")
+    out += [f"    case {i}: otb_uf_{i}(a, b, x, y, z); break;" for i in v3]
+    out.append('    default: *x = *y = *z = nan(""); break;\n    }\n}\n')
     return "\n".join(out)
 
 
@@ -299,6 +447,8 @@ def build_specialised_library(user_funcs, api_only: bool = False) -> pathlib.Pat
     flags = [f'-DOTB_USER_FUNCS_H="{hdr}"']
     build.build_library()
     keep = ("otb_api.cu",) if api_only else ("otb_api.cu", "otb_trace.cu", "otb_render.cu")
+    if any(k == "orient" for k, _, _ in user_funcs):
+        keep += ("otb_gen.cu",)          # the stand-alone generator calls orientation functions too
     base_objs = [build.CSRC / "build" / f.replace(".cu", ".o") for f in build.SOURCES if f not in keep]
     build.build_library(lib, extra_flags=flags, force=True, objdir=objdir, sources=list(keep), extra_objects=base_objs)
     return lib

@@ -33,7 +33,7 @@ def test_library_exports_every_header_symbol():
     assert sorted(_cabi.SYMBOLS) == names
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.otb_abi_version() == 1
+    assert lib.otb_abi_version() == 2
 
 
 def test_struct_layouts_match_the_compiler():

@@ -34,6 +34,21 @@ def saddle_2d_deriv(x, y):
     return 0.02*x + 0.002*y, -0.03*y + 0.002*x
 
 
+def or_func_cone(x, y, f=40.0):
+    """orientation function (ray_source.py:274-276): every ray aims at the point (0, 0, f) in front of its origin"""
+    v = np.column_stack((-x, -y, np.ones_like(x)*f))
+    return v/np.linalg.norm(v, axis=1)[:, np.newaxis]
+
+
+def or_source(ot):
+    """rectangular source with orientation="Function" in front of a detector (generator coverage, a18)"""
+    RT = ot.Raytracer(outline=[-10, 10, -10, 10, -1, 30])
+    RT.add(ot.RaySource(ot.RectangularSurface(dim=[4, 2]), orientation="Function", or_func=or_func_cone,
+                        or_args=dict(f=25.0), pos=[0.5, -1, 0]))
+    RT.add(ot.Detector(ot.RectangularSurface(dim=[8, 8]), pos=[0, 0, 20]))
+    return RT
+
+
 # ---- benchmark configs ---------------------------------------------------------------------------------
 def spherical_aberration(ot):
     """C1: examples/spherical_aberration.py:18-64"""

@@ -146,3 +146,122 @@ def test_image_source(ot):
     g = ot.RaySource(ot.GrayscaleImage(rng.random((8, 8)), [2, 2]), spectrum=ot.LightSpectrum("Monochromatic", wl=600.))
     p, _, _, _, wl = _gen(ot, g, 50_000)
     assert np.all(wl == 600) and np.abs(p[:, :2]).max() <= 1
+
+
+def test_orientation_function(ot):
+    """orientation="Function" (ray_source.py:274-276): or_func(x, y) translated to a device function; the directions
+    the generator produces are exactly or_func evaluated at the generated positions"""
+    import scenes
+    RT = scenes.or_source(ot)           # engine variant with the callable: prebuilt by __graft_entry__.build()
+    N = 100_000
+    rays = RT._generate(np.array([N]), 0, N, 5)
+    p = rays.p0.cpu().numpy().reshape((N, 3), order="F")
+    s = rays.s0.cpu().numpy().reshape((N, 3), order="F")
+    pol = rays.pol0.cpu().numpy().reshape((N, 3), order="F").astype(np.float64)
+    ref = scenes.or_func_cone(p[:, 0], p[:, 1], f=25.0)
+    assert np.max(np.abs(s - ref)) < 1e-15
+    assert np.max(np.abs(np.sum(pol*s, axis=1))) < 1e-6
+    # and through a trace: every ray ends on the outline end plane where its straight line says
+    RT.trace(50_000)
+    P = RT.rays.p_list
+    d = P[:, 1] - P[:, 0]
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    assert np.max(np.abs(d - scenes.or_func_cone(P[:, 0, 0], P[:, 0, 1], f=25.0))) < 1e-12
+    assert RT.detector_image().power() > 0.99
+    with pytest.raises(NotImplementedError):
+        bad = ot.RaySource(ot.Point(), orientation="Function", or_func=lambda x, y: np.random.rand(x.shape[0], 3))
+        RT2 = ot.Raytracer(outline=[-10, 10, -10, 10, -1, 30])
+        RT2.add(bad)
+        RT2.trace(1000)
+
+
+@pytest.mark.parametrize("name", ["double_gauss", "arizona_eye", "image_render", "hurb_square"])
+def test_fused_generation_is_bit_identical(ot, name):
+    """OtbRays.gen_h: rays drawn inside the trace kernel are the rays the generator kernel writes (same device
+    function, same Philox counters), so the whole ray storage and the messages are bit-identical"""
+    import scenes
+    res = []
+    for fused in (False, True):
+        RT = scenes.SCENES[name](ot)
+        RT.fused_generation = fused
+        RT.trace(300_005)        # divisible by the 5 sources of double_gauss: no random remainder split
+        R = RT.rays
+        res.append((R.p_list.copy(), R.s0_list.copy(), R.w_list.copy(), R.n_list.copy(), R.wl_list.copy(),
+                    None if RT.no_pol else R.pol_list.copy(), RT._msgs.copy()))
+    for a, b in zip(*res):
+        if a is not None:
+            assert np.array_equal(a, b, equal_nan=True)
+    # the fused render path (iterative_render) as well: same images from both generation modes
+    imgs = []
+    for fused in (False, True):
+        RT = scenes.SCENES[name](ot)
+        RT.fused_generation = fused
+        RT.ITER_RAYS_STEP = 100_000
+        im = RT.iterative_render(200_000)[0]
+        imgs.append((im.counts.copy(), im.data.copy()))
+    assert np.array_equal(imgs[0][0], imgs[1][0]) and np.allclose(imgs[0][1], imgs[1][1], rtol=1e-12, atol=0)
+
+
+def test_coherent_bundles_are_a_reordering(ot):
+    """Raytracer.coherent_bundles hands the strata of one random variable out in blocks of 32 neighbouring cells:
+    the SET of cells is the same as with the full shuffle (every cell exactly once), neighbouring rays are close in
+    that variable, and the other variables stay decorrelated from it"""
+    N = 320_000
+    out = {}
+    for coh in (False, True):
+        RT = ot.Raytracer(outline=[-1e5, 1e5, -1e5, 1e5, -1e5, 1e5])
+        RT.coherent_bundles = coh
+        RT.add(ot.RaySource(ot.CircularSurface(r=2), divergence="Isotropic", div_angle=10, pos=[0, 0, 0]))
+        rays = RT._generate(np.array([N]), 0, N, 9)
+        out[coh] = (rays.p0.cpu().numpy().reshape((N, 3), order="F"), rays.s0.cpu().numpy().reshape((N, 3), order="F"))
+    N2 = int(np.sqrt(N))
+
+    def cells(s):       # invert the isotropic cone + Shirley map far enough to identify the stratum of the direction
+        r = np.sqrt(np.clip(1 - s[:, 2], 0, None))/np.sin(np.radians(10))          # r in [0, 1]
+        return r
+
+    for coh in (False, True):
+        p, s = out[coh]
+        r = cells(s)
+        # same marginal distributions: r^2 uniform (isotropic cone), uniform disc positions
+        assert abs(np.mean(r**2) - 0.5) < 2e-3 and abs(np.mean(p[:, 0]**2 + p[:, 1]**2) - 2.0) < 5e-3
+        # position and direction stay uncorrelated
+        assert abs(np.corrcoef(p[:, 0], s[:, 0])[0, 1]) < 5e-3 and abs(np.corrcoef(p[:, 1], s[:, 1])[0, 1]) < 5e-3
+    # warp coherence: the spread of the direction inside a group of 32 consecutive rays is a small fraction of the cone
+    sc = out[True][1][:N - N % 32].reshape(-1, 32, 3)
+    ss = out[False][1][:N - N % 32].reshape(-1, 32, 3)
+    spread_c = np.median(np.ptp(sc[:, :, 0], axis=1) + np.ptp(sc[:, :, 1], axis=1))
+    spread_s = np.median(np.ptp(ss[:, :, 0], axis=1) + np.ptp(ss[:, :, 1], axis=1))
+    assert spread_c < 0.15*spread_s, (spread_c, spread_s)
+    # the positions (not the coherent variable here) are not clustered
+    pc = out[True][0][:N - N % 32].reshape(-1, 32, 3)
+    assert np.median(np.ptp(pc[:, :, 0], axis=1)) > 2.0
+
+
+def test_spectra_on_device_match_host_render(ot):
+    """Raytracer.detector_spectrum / source_spectrum (raytracer.py:1100-1132, 1311-1329) binned on the device
+    against LightSpectrum.render (light_spectrum.py:40-79 restated on the host) on the downloaded hits"""
+    import scenes
+    from oracle import spectrum_oracle as so
+    RT = scenes.spherical_aberration(ot)
+    RT.trace(400_000)
+    for src in (None, 1):
+        spec = RT.detector_spectrum(0, source_index=src)
+        hx, hy, hw, wl, *_ = RT._hit_detector(0, src)
+        m = (hw > 0).cpu().numpy()
+        vals, wls = so.render(wl.cpu().numpy()[m], hw.cpu().numpy()[m])
+        assert spec._wls.dtype == wls.dtype and np.array_equal(spec._wls, wls)
+        assert spec._vals.shape == vals.shape and np.allclose(spec._vals, vals, rtol=2e-6, atol=1e-12*vals.max())
+        assert abs(float(np.sum(spec._vals.astype(np.float64))*(wls[1] - wls[0])) - float(hw.sum())) < 1e-5*float(hw.sum())
+    spec = RT.source_spectrum(1)
+    b, e = RT.rays._local_range(1)
+    vals, wls = so.render(RT.rays.wl_list[b:e], RT.rays.w_list[b:e, 0])
+    assert np.array_equal(spec._wls, wls) and np.allclose(spec._vals, vals, rtol=2e-6, atol=1e-12*vals.max())
+    # monochromatic source: the +-1 nm window of light_spectrum.py:66-68
+    RT2 = ot.Raytracer(outline=[-5, 5, -5, 5, -1, 10])
+    RT2.add(ot.RaySource(ot.CircularSurface(r=1), spectrum=ot.LightSpectrum("Monochromatic", wl=555.0), pos=[0, 0, 0]))
+    RT2.add(ot.Detector(ot.RectangularSurface(dim=[4, 4]), pos=[0, 0, 5]))
+    RT2.trace(10_000)
+    spec = RT2.detector_spectrum()
+    vals, wls = so.render(RT2.rays.wl_list, RT2.rays.w_list[:, 0])
+    assert np.array_equal(spec._wls, wls) and np.allclose(spec._vals, vals, rtol=2e-6)

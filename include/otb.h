@@ -418,6 +418,11 @@ int otb_generate_rays(const OtbSource* sources_h, int n_sources, const double* g
                       double* p0_d, double* s0_d, float* pol0_d, float* w0_d, float* wl_d,
                       int32_t* status_d, void* stream);
 
+/* The two standard normal deviates per ray that otb_trace_store / otb_trace_render draw for HURB aperture `slot`
+ * when OtbRays.hurb_z_d is NULL (stand-ins for np.random.normal in Raytracer.__hurb, raytracer.py:468-469): Philox
+ * counter = ray_offset + ray, key = seed.  za_d, zb_d: double[N].  For hosts that replay a device-RNG trace. */
+int otb_hurb_normals(int64_t N, uint64_t seed, int64_t ray_offset, int32_t slot, double* za_d, double* zb_d, void* stream);
+
 /* Detector hits from stored sections: replaces Raytracer._hit_detector (raytracer.py:881-1051)
  * up to and including the sphere projection.  Outputs per ray: projected hit x, y (double),
  * weight (float, 0 = no valid hit).  range_d: double[4] = min x, max x, min y, max y over valid

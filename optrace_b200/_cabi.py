@@ -120,6 +120,7 @@ SYMBOLS = {
     "otb_trace_store": (C.c_int, [_VP, C.POINTER(OtbRays), C.POINTER(OtbRayStore), _VP, _VP, _VP]),
     "otb_generate_rays": (C.c_int, [C.POINTER(OtbSource), C.c_int, _VP, _I64, _U64, _I64, C.c_int,
                                     _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "otb_hurb_normals": (C.c_int, [_I64, _U64, _I64, _I32, _VP, _VP, _VP]),
     "otb_detector_hits": (C.c_int, [C.POINTER(OtbRayStore), _I64, _I64, C.POINTER(OtbDetector),
                                     _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "otb_render_xyzw": (C.c_int, [_VP, _VP, _VP, _VP, _I64, C.POINTER(C.c_double), _I32, _I32, _VP, _VP, _VP]),

@@ -59,9 +59,12 @@ def build_library(out_path=None, extra_flags=(), force=False, objdir=None, sourc
     cc = nvcc()
     srcs = list(sources or SOURCES)
 
+    # variant builds (user callables, scene specialisation) carry no line info: every variant travels to the GPU box
+    flags = NVCC_FLAGS if base_build else [f for f in NVCC_FLAGS if f != "-lineinfo"]
+
     def compile_one(src):
         obj = objdir / (src.replace(".cu", ".o"))
-        r = subprocess.run([cc, *NVCC_FLAGS, *extra_flags, "-c", str(CSRC / src), "-o", str(obj)],
+        r = subprocess.run([cc, *flags, *extra_flags, "-c", str(CSRC / src), "-o", str(obj)],
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

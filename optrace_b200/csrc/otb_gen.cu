@@ -114,3 +114,27 @@ extern "C" int otb_generate_rays(const OtbSource* sources_h, int n_sources, cons
     }
     return OTB_OK;
 }
+
+// The standard normal deviates the trace kernels draw for HURB aperture `slot` (otb_trace.cu store_step): Philox
+// counter = global ray id, stream 0x48555242 ("HURB"), Box-Muller.  Lets a host reproduce a device-RNG trace.
+__global__ void __launch_bounds__(256) hurb_normals_kernel(int64_t N, uint64_t seed, int64_t ray_offset, int slot,
+                                                           double* __restrict__ za, double* __restrict__ zb)
+{
+    for (int64_t k = (int64_t)blockIdx.x*blockDim.x + threadIdx.x; k < N; k += (int64_t)gridDim.x*blockDim.x) {
+        Philox4 rnd = philox4x32_10((uint64_t)(ray_offset + k), 0x48555242u, (uint32_t)slot, seed);
+        double a, b;
+        normal2(rnd, a, b);
+        za[k] = a;
+        zb[k] = b;
+    }
+}
+
+extern "C" int otb_hurb_normals(int64_t N, uint64_t seed, int64_t ray_offset, int32_t slot, double* za_d, double* zb_d, void* stream)
+{
+    if (!za_d || !zb_d || N < 0 || slot < 0) { otb_set_error("invalid argument"); return OTB_ERR_INVALID_ARG; }
+    if (N == 0) return OTB_OK;
+    const int64_t b = (N + 255)/256, cap = 8LL*otb_sm_count();
+    hurb_normals_kernel<<<(int)(b < cap ? b : cap), 256, 0, (cudaStream_t)stream>>>(N, seed, ray_offset, slot, za_d, zb_d);
+    OTB_CUDA(cudaGetLastError());
+    return OTB_OK;
+}

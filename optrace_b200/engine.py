@@ -297,6 +297,16 @@ def trace_render(scene: SceneHandle, rays: DeviceRays, det_recs: list, extents=N
     return msgs.view(_cabi.NMSG, scene.nt)
 
 
+def hurb_normals(lib, N: int, seed: int, ray_offset: int, n_slots: int) -> np.ndarray:
+    """(n_slots, 2, N) standard normal deviates the trace kernels draw for the HURB apertures of a device-RNG trace
+    (otb_hurb_normals): lets the oracle replay exactly that trace"""
+    torch = _torch()
+    out = torch.empty((max(n_slots, 1), 2, max(N, 1)), dtype=torch.float64, device=device())
+    for k in range(n_slots):
+        check(lib.otb_hurb_normals(N, seed, ray_offset, k, dptr(out[k, 0]), dptr(out[k, 1]), stream_ptr()), lib)
+    return out[:n_slots, :, :N].cpu().numpy()
+
+
 def raise_status(st: int):
     if st & 8:
         raise RuntimeError("All ray divergences s need to be in positive z-divergence")

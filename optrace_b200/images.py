@@ -73,6 +73,25 @@ class _BaseImage:
     def Apx(self) -> float:
         return float(self.s[0]*self.s[1]/(self.shape[1]*self.shape[0]))
 
+    def profile(self, x: float = None, y: float = None):
+        """base_image.py:149-186: image cut at x or y (nearest pixel): (bin edges, list of cuts)"""
+        img = self._data
+        if x is not None:
+            if not self.extent[0] <= x <= self.extent[1]:
+                raise ValueError(f"Position x={x} is outside the image x-extent of {self.extent[:2]}")
+            bins = np.linspace(self.extent[2], self.extent[3], self.shape[0] + 1)
+            ind = int((x - self.extent[0])/self.s[0]*self.shape[1]*(1 - 1e-12))
+            iml = [img[:, ind]] if img.ndim == 2 else [img[:, ind, 0], img[:, ind, 1], img[:, ind, 2]]
+        elif y is not None:
+            if not self.extent[2] <= y <= self.extent[3]:
+                raise ValueError(f"Position y={y} is outside the image y-extent of {self.extent[2:]}")
+            bins = np.linspace(self.extent[0], self.extent[1], self.shape[1] + 1)
+            ind = int((y - self.extent[2])/self.s[1]*self.shape[0]*(1 - 1e-12))
+            iml = [img[ind]] if img.ndim == 2 else [img[ind, :, 0], img[ind, :, 1], img[ind, :, 2]]
+        else:
+            raise ValueError("Either x or y parameter must be provided.")
+        return bins, iml
+
 
 class RGBImage(_BaseImage):
     """image/rgb_image.py: [0, 0] is the lower-left pixel, values in [0, 1], 3 channels."""

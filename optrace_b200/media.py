@@ -371,8 +371,10 @@ class LightSpectrum(Spectrum):
             wl0, wl1 = wl.min(), wl.max()
             if np.abs(wl0 - wl1) < 1:
                 wl0, wl1 = max(wl0 - 1, go.wavelength_range[0]), min(wl0 + 1, go.wavelength_range[1])
-            spec._vals, spec._wls = np.histogram(wl, bins=N, weights=w, range=[wl0, wl1])
-            spec._vals = spec._vals*(1/(spec._wls[1] - spec._wls[0]))
+            vals, wls = np.histogram(wl, bins=N, weights=w, range=[wl0, wl1])
+            # Spectrum.__setattr__ (spectrum.py:184-187) stores both as float64 arrays BEFORE the scaling
+            spec._wls = np.asarray(wls, dtype=np.float64)
+            spec._vals = np.asarray(vals, dtype=np.float64)*(1/(spec._wls[1] - spec._wls[0]))
         return spec
 
     @staticmethod
@@ -388,6 +390,6 @@ class LightSpectrum(Spectrum):
             spec._wls = wavelengths(N + 1)
             spec._vals = np.zeros(N, dtype=np.float64)
         else:
-            spec._wls = edges
-            spec._vals = vals.astype(np.float32)*(1/(spec._wls[1] - spec._wls[0]))
+            spec._wls = np.asarray(edges, dtype=np.float64)
+            spec._vals = vals.astype(np.float32).astype(np.float64)*(1/(spec._wls[1] - spec._wls[0]))
         return spec

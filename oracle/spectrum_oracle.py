@@ -20,5 +20,7 @@ def render(wl: np.ndarray, w: np.ndarray, wavelength_range=WAVELENGTH_RANGE):
     if np.abs(wl0 - wl1) < 1:                                   # :70-71
         wl0, wl1 = max(wl0 - 1, wavelength_range[0]), min(wl0 + 1, wavelength_range[1])
     vals, wls = np.histogram(wl, bins=N, weights=w, range=[wl0, wl1])       # :73
+    # assignment to spec._vals / spec._wls converts to float64 (Spectrum.__setattr__, spectrum.py:184-187)
+    vals, wls = np.asarray(vals, dtype=np.float64), np.asarray(wls, dtype=np.float64)
     vals = vals*(1/(wls[1] - wls[0]))                           # :74
     return vals, wls

@@ -247,7 +247,7 @@ def zoo_numeric(ot):
 SCENES = dict(spherical_aberration=spherical_aberration, double_gauss=double_gauss, arizona_eye=arizona_eye,
               image_render=image_render, cosine_surfaces=cosine_surfaces,
               hurb_square=lambda ot: hurb_aperture(ot, "Square"), hurb_pinhole=lambda ot: hurb_aperture(ot, "Pinhole"),
-              hurb_edge=lambda ot: hurb_aperture(ot, "Edge"),
+              hurb_edge=lambda ot: hurb_aperture(ot, "Edge"), hurb_slit=lambda ot: hurb_aperture(ot, "Slit"),
               zoo_analytic=zoo_analytic, zoo_numeric=zoo_numeric)
 
 

@@ -388,11 +388,12 @@ class Raytracer(Group):
         rays = self._generated(scene, N_list, begin, end, seed)
         self._run_trace(scene, rays, N_list, N, begin)
 
-    def trace_rays(self, p, s, pol, w, wl, hurb_z=None, N_list=None) -> None:
+    def trace_rays(self, p, s, pol, w, wl, hurb_z=None, N_list=None, sharded: bool = False) -> None:
         """Extension of the reference API: trace a pre-generated bundle (the arrays RaySource.create_rays
         returns: p, s float64 (N,3); pol (N,3) or None with no_pol; w, wl (N)).  `hurb_z` (n_hurb, 2, N)
         optionally injects the standard normal deviates of the HURB bending.  Used for parity runs on
-        identical bundles."""
+        identical bundles.  `sharded`: under torchrun every rank passes the SAME global bundle
+        and traces its contiguous share of it (dist.shard_range), like trace(N) does with generated rays."""
         N = int(p.shape[0])
         if self._pretrace_check(N):
             return
@@ -402,9 +403,14 @@ class Raytracer(Group):
             pol = None
         elif pol is None:
             raise ValueError("pol is required unless no_pol is set.")
+        begin, end = dist.shard_range(N) if sharded else (0, N)
+        if (begin, end) != (0, N):
+            p, s, w, wl = p[begin:end], s[begin:end], w[begin:end], wl[begin:end]
+            pol = None if pol is None else pol[begin:end]
+            hurb_z = None if hurb_z is None else np.ascontiguousarray(np.asarray(hurb_z)[:, :, begin:end])
         rays = engine.DeviceRays.from_host(p, s, pol, w, wl, hurb_z, seed=int(self.seed))
         N_list = np.array([N]) if N_list is None else np.asarray(N_list, dtype=int)
-        self._run_trace(scene, rays, N_list, N, 0)
+        self._run_trace(scene, rays, N_list, N, begin)
 
     def _run_trace(self, scene, rays, N_list, N_global, begin):
         # drop the previous ray storage first: its device blocks go back to the caching allocator and the new

@@ -7,27 +7,6 @@
 #include "otb_observers.cuh"
 #include "otb_bin.cuh"
 
-// atomic min / max on doubles through compare-and-swap (one call per block)
-__device__ __forceinline__ void atomic_min_d(double* addr, double v)
-{
-    unsigned long long* a = (unsigned long long*)addr;
-    unsigned long long old = *a, assumed;
-    do {
-        assumed = old;
-        if (!(v < __longlong_as_double((long long)assumed))) break;
-        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
-    } while (assumed != old);
-}
-__device__ __forceinline__ void atomic_max_d(double* addr, double v)
-{
-    unsigned long long* a = (unsigned long long*)addr;
-    unsigned long long old = *a, assumed;
-    do {
-        assumed = old;
-        if (!(v > __longlong_as_double((long long)assumed))) break;
-        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
-    } while (assumed != old);
-}
 
 struct DetArgs {
     OtbRayStore st;
@@ -65,7 +44,21 @@ __global__ void __launch_bounds__(128, 6) detector_hits_kernel(const DetArgs a)
         bool no_start = true, no_reach = true;
         int first_ge = -1;
         const double* __restrict__ Pz = P + ray + 2*Nnt;
-        if (monotone && nt <= 4*OTB_DET_COARSE) {
+        // Image planes: a detector behind every tracing surface is reached in the LAST section by every ray.  With z
+        // monotone along the rays (reported by the trace) a second last point in front of z_min says so for this ray
+        // with two loads instead of the search over the sections below.
+        double z_prev = 0.0, z_last = 0.0;
+        bool last_section = false;
+        if (monotone && nt >= 2) {
+            z_prev = __ldcs(Pz + N*(int64_t)(nt - 2));
+            z_last = __ldcs(Pz + N*(int64_t)(nt - 1));
+            last_section = z_prev < S.z_min;
+        }
+        if (last_section) {
+            no_start = false;
+            no_reach = !(z_last >= S.z_min);           // z_max >= z_min: both comparisons of the scan fail together
+            first_ge = (z_last >= S.z_min) ? nt - 1 : -1;
+        } else if (monotone && nt <= 4*OTB_DET_COARSE) {
             // z never decreases along a ray (reported by the trace): two batches of independent loads instead of
             // a scan over all nt sections or a bisection of dependent loads (the kernel is bound by the number
             // of DRAM round trips per ray, not by bytes): every 4th section plus the last one, then the three
@@ -180,10 +173,10 @@ __global__ void __launch_bounds__(128, 6) detector_hits_kernel(const DetArgs a)
             mxy = fmax(smax_y[0], smax_y[k]); smax_y[0] = mxy;
         }
         if (smin_x[0] <= smax_x[0]) {
-            atomic_min_d(&a.range[0], smin_x[0]);
-            atomic_max_d(&a.range[1], smax_x[0]);
-            atomic_min_d(&a.range[2], smin_y[0]);
-            atomic_max_d(&a.range[3], smax_y[0]);
+            atomic_min_double(&a.range[0], smin_x[0]);
+            atomic_max_double(&a.range[1], smax_x[0]);
+            atomic_min_double(&a.range[2], smin_y[0]);
+            atomic_max_double(&a.range[3], smax_y[0]);
         }
         if (sill) atomicAdd(a.ill, (unsigned long long)sill);
     }

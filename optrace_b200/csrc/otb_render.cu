@@ -46,26 +46,6 @@ struct DetState {
     bool started, finished, ok, all_start, all_noreach;
 };
 
-__device__ __forceinline__ void atomic_min_dd(double* addr, double v)
-{
-    unsigned long long* a = (unsigned long long*)addr;
-    unsigned long long old = *a, assumed;
-    do {
-        assumed = old;
-        if (!(v < __longlong_as_double((long long)assumed))) break;
-        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
-    } while (assumed != old);
-}
-__device__ __forceinline__ void atomic_max_dd(double* addr, double v)
-{
-    unsigned long long* a = (unsigned long long*)addr;
-    unsigned long long old = *a, assumed;
-    do {
-        assumed = old;
-        if (!(v > __longlong_as_double((long long)assumed))) break;
-        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
-    } while (assumed != old);
-}
 
 // one sequential step of the fused mode: trace, book messages, then the detector walk of _hit_detector
 // (raytracer.py:881-1051) online on section i = (p_i -> r.p) while it is still in registers
@@ -232,10 +212,10 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
                 mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, k));
             }
             if ((threadIdx.x & 31) == 0 && mnx <= mxx) {
-                atomic_min_dd(&a.dets[d].range[0], mnx);
-                atomic_max_dd(&a.dets[d].range[1], mxx);
-                atomic_min_dd(&a.dets[d].range[2], mny);
-                atomic_max_dd(&a.dets[d].range[3], mxy);
+                atomic_min_double(&a.dets[d].range[0], mnx);
+                atomic_max_double(&a.dets[d].range[1], mxx);
+                atomic_min_double(&a.dets[d].range[2], mny);
+                atomic_max_double(&a.dets[d].range[3], mxy);
             }
         }
     }

@@ -118,6 +118,7 @@ def cpu_bundle(N, seed=7):
 
 
 def run_cpu(args, steps, warmup, rays):
+    """fallback CPU arm: the numpy oracle port (only when the reference did not travel with the snapshot)"""
     import optrace_b200 as ot
     from optrace_b200 import color
     from optrace_b200.scene import flatten_raytracer, detector_record
@@ -137,6 +138,61 @@ def run_cpu(args, steps, warmup, rays):
         _, used = cpu_step(fs, det, color.OBSERVERS, bundle, T)
     dt = (time.perf_counter() - t0)/steps
     return rays*(fs.nt - 1)/dt, dt, used, fs.nt
+
+
+REF_RAYS = 1_000_000         # N_cpu = 1e6 rays per trace, the size of tests/benchmark.py
+
+
+def run_reference(steps, warmup, budget_s=150.0):
+    """The UNMODIFIED reference (oracle/_ref, imported through oracle/ref_loader.py) on the host cores, timed with
+    its own method (time.perf_counter around RT.trace(N), tests/benchmark.py:81-86) plus RT.detector_image():
+    multithreading on, PYTHON_CPU_COUNT = min(cores, 64) (the reference rejects more, misc.py:27-28), 1e6 rays per
+    step — fewer only when steps + warmup of that size would not fit the time budget on this host.
+    Returns (ray*surfaces/s, s per step, threads, nt, rays per step, trace-only ray*surfaces/s)."""
+    from oracle import ref_loader
+    T = cpu_threads()
+    os.environ["PYTHON_CPU_COUNT"] = str(T)
+    ot = ref_loader.load()
+    import scenes
+    ot.global_options.multithreading = True
+    ot.global_options.show_progress_bar = False
+    ot.global_options.show_warnings = False
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        RT = scenes.double_gauss(ot)
+        t0 = time.perf_counter()
+        RT.trace(200_000)                       # sizes the sample: rays per second of this host
+        RT.detector_image()
+        rate = 200_000/(time.perf_counter() - t0)
+        rays = int(min(REF_RAYS, max(100_000, rate*budget_s/max(1, steps + warmup))))
+        for _ in range(warmup):
+            RT.trace(rays)
+            RT.detector_image()
+        tt = 0.0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            a = time.perf_counter()
+            RT.trace(rays)
+            tt += time.perf_counter() - a
+            RT.detector_image()
+        dt = (time.perf_counter() - t0)/steps
+    nt = RT.rays.Nt
+    return rays*(nt - 1)/dt, dt, T, nt, rays, rays*(nt - 1)/(tt/steps)
+
+
+def reference_or_port(steps, warmup, budget_s):
+    """(value, s per step, threads, nt, rays per step, kind, sample text): the reference itself when it travelled
+    with the snapshot, else the numpy oracle port (same formulas, same thread scheme)"""
+    from oracle import ref_loader
+    if ref_loader.available():
+        v, dt, T, nt, rays, vt = run_reference(steps, warmup, budget_s)
+        return v, dt, T, nt, rays, "reference", (
+            f"unmodified reference (oracle/_ref), Raytracer.trace({rays}) + detector_image() per step, multithreading on, "
+            f"PYTHON_CPU_COUNT={T}; {steps} steps, {dt*steps:.1f} s; trace alone {1e9/vt:.1f} ms/surface/Mray "
+            f"(sections; the reference's benchmark divides by sections - 1)")
+    v, dt, used, nt = run_cpu(None, steps, min(warmup, 1), CPU_SAMPLE_RAYS)
+    return v, dt, used, nt, CPU_SAMPLE_RAYS, "port", (f"{CPU_SAMPLE_RAYS} rays per step, trace + detector image, numpy oracle port "
+                                                     f"of the reference with its thread scheme (reference not vendored)")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -389,12 +445,9 @@ def run_gpu(args):
             "clocks": clk,
         }
         if not args.no_cpu and world == 1:
-            CPU_STEPS = 24      # ~10 s of host work: 24 bundles of CPU_SAMPLE_RAYS rays through the same scene
-            v, dt, used, _ = run_cpu(args, CPU_STEPS, 1, CPU_SAMPLE_RAYS)
-            line["cpu_baseline"] = {"value": v, "unit": "ray*surface/s", "cores": used, "kind": "port",
-                                    "sample": f"{CPU_STEPS} x {CPU_SAMPLE_RAYS} rays of the same scene, trace + detector "
-                                              f"image, {dt*CPU_STEPS:.1f} s in total; numpy oracle port, reference "
-                                              f"thread scheme",
+            # ~15 s of host work on the same scene, the reference itself when it travelled with the snapshot
+            v, dt, used, _, rays_cpu, kind, sample = reference_or_port(3, 1, 20.0)
+            line["cpu_baseline"] = {"value": v, "unit": "ray*surface/s", "cores": used, "kind": kind, "sample": sample,
                                     "ms_per_surface_per_Mray": 1e9/v}
         print(json.dumps(line))
     if world > 1:
@@ -406,17 +459,17 @@ def main():
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
-        rays = CPU_SAMPLE_RAYS
-        v, dt, used, nt = run_cpu(args, max(1, args.steps), min(args.warmup, 1), rays)
+        v, dt, used, nt, rays, kind, sample = reference_or_port(max(1, args.steps), args.warmup, 150.0)
         print(json.dumps({
             "impl": "reference", "metric": "ray-surfaces/s", "value": v, "unit": "ray*surface/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt*1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "double_gauss (BASELINE configs[1]) on the host CPU: bounded sample per step",
-                       "rays_per_step": rays, "nt": nt},
-            "cpu_baseline": {"value": v, "unit": "ray*surface/s", "cores": used, "kind": "port",
-                             "sample": f"{rays} rays per step, trace + detector image, numpy oracle port of the "
-                                       f"reference with its thread scheme"},
+            "config": {"workload": "double_gauss (BASELINE configs[1]): 14 spherical + ring aperture + end absorber, "
+                                   "7 Abbe media, 5 point sources D65, polarisation on, store mode + detector image "
+                                   "— on the host CPU, bounded sample per step",
+                       "rays_per_step": rays, "nt": nt, "sections_traced": nt - 1},
+            "cpu_baseline": {"value": v, "unit": "ray*surface/s", "cores": used, "kind": kind, "sample": sample,
+                             "ms_per_surface_per_Mray": 1e9/v},
             "e2e": {"value": v, "unit": "ray*surface/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     run_gpu(args)

@@ -14,7 +14,8 @@ from .surfaces import (Surface, Point, Line, CircularSurface, RectangularSurface
                        FunctionSurface2D, DataSurface1D, DataSurface2D)
 from .media import Spectrum, LightSpectrum, TransmissionSpectrum, RefractionIndex  # noqa: F401
 from .images import RGBImage, GrayscaleImage, ScalarImage, RenderImage  # noqa: F401
-from .elements import Element, Lens, IdealLens, Filter, Aperture, Detector, RaySource, Group  # noqa: F401
+from .elements import Element, Lens, IdealLens, Filter, Aperture, Detector, RaySource, Group, PointMarker  # noqa: F401
+from .load import load_agf, load_zmx  # noqa: F401
 from .ray_storage import RayStorage  # noqa: F401
 from .raytracer import Raytracer  # noqa: F401
 from . import presets, color  # noqa: F401

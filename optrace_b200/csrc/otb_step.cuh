@@ -268,11 +268,11 @@ __device__ __forceinline__ void trace_step(const KScene& sc, const double* __res
     bool done = false;
     if (st.role <= OTB_STEP_LENS_BACK && S.kind == OTB_SURF_CONIC) {
         if (sc.arithmetic == OTB_ARITH_RELAXED) {
-            if (S.par[OTB_P_K] == 0.0) done = relaxed_conic_lens_step<POL, true>(sc, st, S, r, fl, status);
-            else done = relaxed_conic_lens_step<POL, false>(sc, st, S, r, fl, status);
+            if (S.par[OTB_P_K] == 0.0) done = relaxed_conic_lens_step<POL, true>(sc, aux, st, S, r, fl, status);
+            else done = relaxed_conic_lens_step<POL, false>(sc, aux, st, S, r, fl, status);
         } else {
-            if (S.par[OTB_P_K] == 0.0) done = fast_conic_lens_step<POL, true>(sc, st, S, r, fl, status);
-            else done = fast_conic_lens_step<POL, false>(sc, st, S, r, fl, status);
+            if (S.par[OTB_P_K] == 0.0) done = fast_conic_lens_step<POL, true>(sc, aux, st, S, r, fl, status);
+            else done = fast_conic_lens_step<POL, false>(sc, aux, st, S, r, fl, status);
         }
     } else if (st.role == OTB_STEP_APERTURE && !st.hurb && (S.flags & OTB_SF_FLAT) && !(S.flags & OTB_SF_ROTATED)
                && (S.kind == OTB_SURF_CIRCLE || S.kind == OTB_SURF_RECT || S.kind == OTB_SURF_RING)) {

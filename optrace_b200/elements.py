@@ -194,6 +194,23 @@ class Aperture(Element):
         super().__init__(surface, pos, **kwargs)
 
 
+class PointMarker(Element):
+    """geometry/marker/point_marker.py: text / point annotation of a geometry (an Element on a Point); carried
+    through Group bookkeeping (the .zmx importer labels its groups with one), ignored by the tracer"""
+    abbr = "M"
+    _allow_non_2D = True
+
+    def __init__(self, desc: str, pos, text_factor: float = 1., marker_factor: float = 1., label_only: bool = False,
+                 **kwargs):
+        for nm, v in (("text_factor", text_factor), ("marker_factor", marker_factor)):
+            if not isinstance(v, (int, float)) or isinstance(v, bool):
+                raise TypeError(f"{nm} needs to be a number.")
+        if not isinstance(label_only, bool):
+            raise TypeError("label_only needs to be bool.")
+        self.marker_factor, self.text_factor, self.label_only = marker_factor, text_factor, label_only
+        super().__init__(Point(), pos, desc=desc, **kwargs)
+
+
 class Detector(Element):
     """geometry/detector.py"""
     abbr = "DET"
@@ -491,6 +508,8 @@ class Group(_Shape):
             self.detectors.append(el)
         elif isinstance(el, Lens):
             self.lenses.append(el)
+        elif isinstance(el, PointMarker):
+            self.markers.append(el)
         elif isinstance(el, Group):
             if self.n0 != el.n0:
                 warning("Overwriting ambient index with index from new Group.")

@@ -106,6 +106,18 @@ class RGBImage(_BaseImage):
         return d
 
 
+    def to_grayscale_image(self) -> "GrayscaleImage":
+        """rgb_image.py:41-56: luminance Y of the linearised sRGB values (Y row of the sRGB -> XYZ matrix,
+        color/srgb.py:61-63), gamma-compressed back and clipped to [0, 1]"""
+        from . import color
+        lin = color.srgb_to_srgb_linear(self._data)
+        Y = 0.2126729*lin[:, :, 0] + 0.7151522*lin[:, :, 1] + 0.0721750*lin[:, :, 2]
+        low = np.abs(Y) <= 0.0031308
+        g = np.where(low, 12.92*Y, np.sign(Y)*(1.055*np.abs(Y)**(1/2.4) - 0.055))
+        return GrayscaleImage(np.clip(g, 0, 1), extent=self.extent, desc=self.desc, long_desc=self.long_desc,
+                              quantity=self.quantity, projection=self.projection, limit=self.limit)
+
+
 class ScalarImage(_BaseImage):
     """image/scalar_image.py: one channel, non-negative values (irradiance, illuminance, CIELUV channels ...)"""
     _channels = 1

@@ -20,7 +20,7 @@ from .media import RefractionIndex, LightSpectrum
 from .options import global_options, warning
 from .ray_storage import RayStorage, split_rays
 from .scene import flatten_raytracer, detector_record
-from .surfaces import RingSurface, SlitSurface, SphericalSurface
+from .surfaces import RectangularSurface, RingSurface, SlitSurface, SphericalSurface
 from ._state import state_of
 from . import _state
 from . import color
@@ -160,38 +160,103 @@ class Raytracer(Group):
                     nm = names[s] if s < len(names) else "?"
                     warning(f"{count} rays ({100*count/N:.3g}% of all rays) " + text[t].format(s=s, n=nm))
 
-    # -- geometry checks (raytracer.py:510-578, without the sampled collision test) --------------------
+    # -- geometry checks (raytracer.py:510-664) ---------------------------------------------------------------
+    @staticmethod
+    def check_collision(front, back, res: int = 100):
+        """Raytracer.check_collision (raytracer.py:581-664): does `front` reach behind `back` somewhere both are
+        defined?  Returns (collision flag, x, y, z arrays of the colliding samples).  Point / line against surface:
+        the surface height at the point(s); surface against surface: a res x res grid over the overlap of the two
+        xy extents, compared where both masks hold.  Scene-setup sampling on the host (1e4 samples per pair)."""
+        from .surfaces import Surface, Point, Line
+        none = (False, np.array([]), np.array([]), np.array([]))
+        if not (isinstance(front, Surface) or isinstance(back, Surface)):
+            raise TypeError("At least one object needs to be a Surface for collision detection")
+        for kind in (Point, Line):
+            if isinstance(front, kind) or isinstance(back, kind):
+                first = isinstance(front, kind)           # the point / line is the object in front
+                obj, surf = (front, back) if first else (back, front)
+                if kind is Point:
+                    x, y = np.array([obj.pos[0]]), np.array([obj.pos[1]])
+                else:
+                    t = np.linspace(-obj.r, obj.r, 10*res)
+                    x, y = obj.pos[0] + np.cos(obj.angle)*t, obj.pos[1] + np.sin(obj.angle)*t
+                z = np.asarray(surf.values(x, y), dtype=np.float64)
+                bad = ((z < obj.pos[2]) if first else (z > obj.pos[2])) & surf.mask(x, y)
+                k = np.nonzero(bad)[0]
+                return bool(bad.any()), x[k], y[k], z[k]
+        ef, eb = front.extent, back.extent
+        if ef[5] < eb[4]:                                  # z extents apart
+            return none
+        x0, x1, y0, y1 = max(ef[0], eb[0]), min(ef[1], eb[1]), max(ef[2], eb[2]), min(ef[3], eb[3])
+        if x0 > x1 or y0 > y1:                             # no common area in the xy projection
+            return none
+        Y, X = np.mgrid[y0:y1:res*1j, x0:x1:res*1j]
+        x, y = X.flatten(), Y.flatten()
+        both = front.mask(x, y) & back.mask(x, y)
+        x, y = x[both], y[both]
+        zf = np.asarray(front.values(x, y), dtype=np.float64)
+        zb = np.asarray(back.values(x, y), dtype=np.float64)
+        k = np.nonzero(zf > zb)[0]
+        return bool(k.shape[0]), x[k], y[k], zf[k]
+
+    def _tracing_elements(self):
+        """z-ordered Lens / Filter / Aperture elements plus the end absorber at the outline (raytracer.py:492-508)"""
+        o = self.outline
+        end = Aperture(RectangularSurface(dim=[o[1] - o[0], o[3] - o[2]]), pos=[(o[1] + o[0])/2, (o[2] + o[3])/2, o[5]])
+        return [el for el in self.elements if isinstance(el, (Lens, Filter, Aperture))] + [end]
+
     def _geometry_checks(self) -> None:
+        """Raytracer.__geometry_checks (raytracer.py:510-578): elements and sources inside the outline, surfaces in
+        sequence without collisions (front | back of every element, every element | the next one, sources | first
+        element), HURB only on ring / slit apertures.  Sets geometry_error and fault_pos."""
         o = self.outline + self.N_EPS*np.array([-1, 1, -1, 1, -1, 1])
 
         def inside(e):
             return o[0] <= e[0] and e[1] <= o[1] and o[2] <= e[2] and e[3] <= o[3] and o[4] <= e[4] and e[5] <= o[5]
 
-        if not self.ray_sources:
-            warning("RaySource Missing.")
+        def fail(msg=None):
+            if msg:
+                warning(msg)
             self.geometry_error = True
-            return
-        els = [el for el in self.elements if isinstance(el, (Lens, Filter, Aperture))]
+
+        if not self.ray_sources:
+            return fail("RaySource Missing.")
+        els = self._tracing_elements()
+        hit = None
         for i, el in enumerate(els):
             if not inside(el.extent):
-                warning(f"Element{i} {el} with extent {el.extent} outside outline {self.outline}.")
-                self.geometry_error = True
-                return
-            if self.use_hurb and isinstance(el, Aperture) and not isinstance(el.front, (RingSurface, SlitSurface)):
-                warning(f"Ray bending for surface type {type(el.front).__name__} not implemented.")
-                self.geometry_error = True
-                return
-        prev_z = -np.inf
-        for el in els:       # z-ordering of consecutive surfaces (coarse stand-in for check_collision)
-            for sf in ([el.front, el.back] if el.has_back() and not getattr(el, "is_ideal", False) else [el.front]):
-                if sf.z_min < prev_z - 1e-9 and sf.is_flat():
-                    pass
-                prev_z = max(prev_z, sf.pos[2])
-        for rs in self.ray_sources:
-            if not inside(rs.extent):
-                warning(f"RaySource {rs} with extent {rs.extent} outside outline {self.outline}.")
-                self.geometry_error = True
-                return
+                return fail(f"Element{i} {el} with extent {el.extent} outside outline {self.outline}.")
+            pairs = []
+            if i + 1 < len(els):
+                pairs.append((el.front, els[i + 1].front))
+            if el.has_back():
+                pairs.append((el.front, el.back))
+                pairs.append((el.back, els[i + 1].front))
+            for a, b in pairs:
+                c = self.check_collision(a, b)
+                if c[0]:
+                    hit = c
+                    break
+            if self.use_hurb and i < len(els) - 1 and isinstance(el, Aperture) \
+                    and not isinstance(el.front, (RingSurface, SlitSurface)):
+                return fail(f"Ray bending for surface type {type(el.front).__name__} not implemented.")
+            if hit:
+                break
+        if not hit:
+            for rs in self.ray_sources:
+                if not inside(rs.extent):
+                    return fail(f"RaySource {rs} with extent {rs.extent} outside outline {self.outline}.")
+                if rs.pos[2] >= els[0].extent[4]:
+                    c = self.check_collision(rs.surface, els[0].front)
+                    if c[0]:
+                        hit = c
+                        break
+        if hit:
+            _, xc, yc, zc = hit
+            fail(f"Detected collision between two Surfaces at {xc[0], yc[0], zc[0]}"
+                 f" and at least {xc.shape[0]} other positions.")
+            self.fault_pos = np.column_stack((xc, yc, zc))
+            return
         self.geometry_error = False
 
     def _pretrace_check(self, N) -> bool:

@@ -244,11 +244,57 @@ def zoo_numeric(ot):
     return RT
 
 
+def microscope(ot, no_pol=False):
+    """the reference's own benchmark scene (tests/benchmark.py:16-66): 60x microscope objective + tube lens (.zmx),
+    eyepiece (.zmx), Arizona eye model, cell image source — 57 tracing surfaces, glasses from four .agf catalogues.
+    The resource files travel with the vendored reference (oracle/_ref, tools/vendor_reference.py); the element
+    positions the reference derives with its paraxial analysis (TMA, out of scope here) come from the fixture
+    tests/golden/load_zmx.json (tools/gen_golden_load.py)."""
+    import json
+    import pathlib
+    root = pathlib.Path(__file__).resolve().parent.parent
+    res = root / "oracle" / "_ref" / "examples" / "resources"
+    if not res.exists():
+        res = pathlib.Path("/root/reference/examples/resources")
+    pos = json.loads((root / "tests" / "golden" / "load_zmx.json").read_text())["benchmark"]
+    RT = ot.Raytracer(outline=[-50, 50, -50, 50, -30, 430], no_pol=no_pol)
+    RT.add(ot.RaySource(ot.presets.image.cell([100e-3, 100e-3]), divergence="Lambertian", pos=[0, 0, -0.00000001],
+                        s=[0, 0, 1], div_angle=50, desc="Cell"))
+    n_dict = {}
+    for f in ("schott", "ohara", "hikari", "hoya"):
+        n_dict |= ot.load_agf(str(res / "materials" / f"{f}.agf"))
+    G = ot.load_zmx(str(res / "microscope" / "Nikon_1p25NA_60x_US7889433B2_MultiConfig_v2.zmx"), n_dict=n_dict)
+    RT.n0 = G.n0
+    RT.add(ot.Group(G.lenses[:18]))
+    tube = ot.Group(G.lenses[20:24])
+    tube.move_to(pos["tube_pos"])
+    RT.add(tube)
+    eyepiece = ot.load_zmx(str(res / "eyepiece" / "UK565851-1.zmx"), n_dict=n_dict)
+    eyepiece.remove(eyepiece.detectors)
+    eyepiece.move_to(pos["eyepiece_pos"])
+    RT.add(eyepiece)
+    eye = ot.presets.geometry.arizona_eye()
+    eye.move_to(pos["eye_pos"])
+    RT.add(eye)
+    return RT
+
+
+def microscope_available() -> bool:
+    import pathlib
+    root = pathlib.Path(__file__).resolve().parent.parent
+    return (root / "oracle" / "_ref" / "examples" / "resources").exists() or pathlib.Path("/root/reference/examples/resources").exists()
+
+
 SCENES = dict(spherical_aberration=spherical_aberration, double_gauss=double_gauss, arizona_eye=arizona_eye,
               image_render=image_render, cosine_surfaces=cosine_surfaces,
               hurb_square=lambda ot: hurb_aperture(ot, "Square"), hurb_pinhole=lambda ot: hurb_aperture(ot, "Pinhole"),
               hurb_edge=lambda ot: hurb_aperture(ot, "Edge"), hurb_slit=lambda ot: hurb_aperture(ot, "Slit"),
               zoo_analytic=zoo_analytic, zoo_numeric=zoo_numeric)
+
+
+# the reference's benchmark scene needs the .zmx / .agf files that travel with the vendored reference
+if microscope_available():
+    SCENES["microscope"] = microscope
 
 
 # ---- known-answer surfaces of the reference's own tests (tests/test_surface.py:158-174, 204-219) -----------

@@ -265,3 +265,41 @@ def test_spectra_on_device_match_host_render(ot):
     spec = RT2.detector_spectrum()
     vals, wls = so.render(RT2.rays.wl_list, RT2.rays.w_list[:, 0])
     assert np.array_equal(spec._wls, wls) and np.allclose(spec._vals, vals, rtol=2e-6)
+
+
+@pytest.mark.parametrize("preset", ["tv_testcard2", "ETDRS_chart_inverted"])
+def test_reference_image_presets_pixel_sampling(ot, preset):
+    """C3 / C4 sources (examples/arizona_eye_model.py, image_render_many_rays.py) on the reference's OWN images
+    (optrace_b200/data/images = optrace/resources/images): generated positions follow the linear-light pixel power
+    (ray_source.py:237-255, random.py:129-140), pixel by pixel; RGB images also the channel mixing (srgb.py:513-553)"""
+    from optrace_b200 import color
+    im = getattr(ot.presets.image, preset)([4, 3])
+    RS = ot.RaySource(im, pos=[0, 0, 0])
+    N = 4_000_000
+    p, s, pol, w, wl = _gen(ot, RS, N)
+    H, W = im.shape[:2]
+    PX = np.clip(np.floor((p[:, 0] + 2)/4*W).astype(int), 0, W - 1)
+    PY = np.clip(np.floor((p[:, 1] + 1.5)/3*H).astype(int), 0, H - 1)
+    cnt = np.zeros((H, W))
+    np.add.at(cnt, (PY, PX), 1)
+    data = im.data
+    if data.ndim == 3:
+        pw = color.power_from_srgb_linear(color.srgb_to_srgb_linear(data))
+    else:
+        pw = color.srgb_to_srgb_linear(data)          # grayscale: pixel value through the sRGB curve (ray_source.py:120-144)
+    pw = pw/pw.sum()
+    assert np.all(cnt[pw == 0] == 0)                   # black pixels never emit
+    # stratified inverse-CDF sampling: a pixel owns an interval of the CDF axis, the N strata cut it with at most one
+    # partial stratum at either end — every count within two of its expectation N p (plain sampling: ~sqrt(N p))
+    assert np.max(np.abs(cnt - N*pw)) <= 2.0 + 1e-6
+    assert np.mean(np.abs(cnt - N*pw)[pw > 0]) < 0.6
+    if data.ndim == 3:
+        # wavelengths: mean power share of the three primaries over the whole image
+        lin = color.srgb_to_srgb_linear(data)
+        share = np.array([color.SRGB_R_PRIMARY_POWER_FACTOR*lin[..., 0].sum(), color.SRGB_G_PRIMARY_POWER_FACTOR*lin[..., 1].sum(),
+                          color.SRGB_B_PRIMARY_POWER_FACTOR*lin[..., 2].sum()])
+        share /= share.sum()
+        # the primaries overlap: compare the mean wavelength with the mixture of the primaries' mean wavelengths
+        wl5, Fr, Fg, Fb = color.srgb_primary_cdfs()
+        means = [np.sum(0.5*(wl5[1:] + wl5[:-1])*np.diff(F))/F[-1] for F in (Fr, Fg, Fb)]
+        assert abs(wl.mean() - float(np.dot(share, means))) < 0.3

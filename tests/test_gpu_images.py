@@ -109,7 +109,7 @@ def test_resolution_filter_matches_reference(ot, scene):
     img2.render(g["det0_ph"], g["det0_w"], g["det0_wl"], limit=limit, _dont_filter=True)
     assert abs(img2.power() - float(np.sum(g["det0_w"].astype(np.float64)))) < 1e-9
     img2._apply_rayleigh_filter()
-    assert np.array_equal(img2.data, d)
+    assert np.allclose(img2.data, d, rtol=1e-11, atol=1e-14*d.max())      # atomic accumulation order differs between two renders
     img3 = ot.RenderImage(extent=g["det0_extent0"], projection="Equidistant")
     with pytest.raises(RuntimeError):
         img3.render(g["det0_ph"], g["det0_w"], g["det0_wl"], limit=limit)

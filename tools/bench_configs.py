@@ -22,6 +22,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--rays", type=int, default=10_000_000)
 ap.add_argument("--cpu-rays", type=int, default=100_000)
 ap.add_argument("--out", default="gpurun_out/configs.json")
+ap.add_argument("--only", default="", help="comma separated scene names")
 args = ap.parse_args()
 engine.ensure_init()
 ot.global_options.show_warnings = False
@@ -43,7 +44,14 @@ CASES = [(n, m, False) for n, m in (("spherical_aberration", "store"), ("double_
                                     ("image_render", "fused6"), ("cosine_surfaces", "store"), ("hurb_square", "store"),
                                     ("hurb_pinhole", "store"), ("zoo_analytic", "store"), ("zoo_numeric", "store"))]
 CASES += [(n, m, True) for n, m in (("double_gauss", "store"), ("arizona_eye", "store"), ("image_render", "fused6"))]
+# the reference's own published benchmark (tests/benchmark.py: 57 surfaces, 1 M rays, with and without polarisation;
+# README.md:45 / docs testing.rst:94-113: 85 / 53 ms per surface per Mray on 4 cores of an i7-1360P)
+if "microscope" in scenes.SCENES:
+    CASES += [("microscope", "store", False), ("microscope_no_pol", "store", False)]
+    scenes.SCENES["microscope_no_pol"] = lambda o: scenes.microscope(o, no_pol=True)
 for name, mode, want_spec in CASES:
+    if args.only and name not in args.only.split(","):
+        continue
     RT = scenes.SCENES[name](ot)
     RT.use_specialised_kernels = want_spec
     spec = RT.compile() if want_spec else False
@@ -80,7 +88,13 @@ for name, mode, want_spec in CASES:
     t0 = time.perf_counter()
     orc.detector_hits(out, rec)
     t_cpu_det = time.perf_counter() - t0
-    row = dict(scene=name, mode=mode, nt=nt, rays=N, no_pol=RT.no_pol, specialised=bool(spec),
+    extra = {}
+    if name.startswith("microscope"):
+        # the reference's metric: seconds of RT.trace(N) / len(RT.tracing_surfaces) / Mrays (tests/benchmark.py:81-86)
+        extra = dict(reference_metric_ms_per_surface_per_Mray=t_tr*1e3/len(RT.tracing_surfaces)/(N/1e6),
+                     published_ms_per_surface_per_Mray=dict(pol_4cores=85, no_pol_4cores=53, pol_1core=218, no_pol_1core=148,
+                                                            best_no_pol_12cores=43))
+    row = dict(scene=name, mode=mode, nt=nt, rays=N, no_pol=RT.no_pol, specialised=bool(spec), **extra,
                gpu_step_ms=t*1e3, gpu_trace_ms=None if t_tr is None else t_tr*1e3,
                gpu_ray_surfaces_per_s=N*(nt - 1)/t,
                gpu_trace_only_ray_surfaces_per_s=None if t_tr is None else N*(nt - 1)/t_tr,

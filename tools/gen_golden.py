@@ -38,7 +38,7 @@ DEFAULT_N = 2000
 if os.environ.get("GOLDEN_N"):
     # 1e5 rays for the BASELINE config scenes ("frozen bundles of 1e5 rays per config"); the two
     # coverage scenes (20 and 12 sections) stay at 3e4 so that the snapshot sent to the GPU box keeps below its limit
-    N_RAYS, DEFAULT_N = dict(zoo_analytic=30000, zoo_numeric=30000), int(os.environ["GOLDEN_N"])
+    N_RAYS, DEFAULT_N = dict(zoo_analytic=30000, zoo_numeric=30000, microscope=10000), int(os.environ["GOLDEN_N"])
 OUT_DIR = pathlib.Path(os.environ.get("GOLDEN_DIR", ROOT / "tests" / "golden"))
 LARGE = bool(os.environ.get("GOLDEN_N"))
 

@@ -382,6 +382,7 @@ def run_gpu(args):
         step_e2e()
     # the last image is on the host (rank 0) / complete on the device (other ranks) inside the timed region as well
     out = prev._materialise() if rank == 0 else prev._wait_device()
+    d2h_bytes = int(prev.transferred_bytes) if rank == 0 else 0
     t1.record()
     barrier()
     e2e_ms = max(t0.elapsed_time(t1), (time.perf_counter() - w0)*1e3)/args.steps
@@ -438,9 +439,11 @@ def run_gpu(args):
                          "kernel": "trace_store_kernel<POL, LENS>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "e2e": {"value": units/(e2e_ms*1e-3), "unit": "ray*surface/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out.nbytes),
-                    "pipelining": "image download of step k overlaps the trace of step k+1 (depth 1); N > 1: the "
-                                  "all-reduced image is read back on rank 0"},
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h_bytes,
+                    "image_bytes_dense": int(out.nbytes),
+                    "pipelining": "image download of step k overlaps the trace of step k+1 (depth 1); only the occupied "
+                                  "32 x 32 tiles of the histogram travel (otb_tiles.cu), over NVLink and over PCIe; "
+                                  "N > 1: the all-reduced image is read back on rank 0"},
             "gpu_launches": 8*args.steps,     # generate, trace_store, detector_hits, render x (resident + e2e region)
             "clocks": clk,
         }

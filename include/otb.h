@@ -405,6 +405,22 @@ int otb_image_stats(const double* img_d, int64_t npx, int32_t pass, double param
 int otb_image_convert(const double* img_d, int64_t npx, int32_t mode, double scale, double chroma_scale,
                       const double* stats_d, double* out_d, void* stream);
 
+/* ---- sparse transport of detector images (otb_tiles.cu) --------------------------------------------------------
+ * A (Ny, Nx, 4) histogram of an imaging system is a few per cent non-zero; the all-reduce over the GPUs of a
+ * sharded trace (the reference has no counterpart) and the device -> host copy behind
+ * RenderImage.data move only the occupied T x T pixel tiles:
+ *   mask:   mask_d[ty*ntx + tx] = 1 where the tile holds a non-zero value (never cleared: the caller zeroes it, and
+ *           MAX-all-reduces it over the ranks to obtain the union)
+ *   pack:   header_d[0] = number of tiles in the mask, header_d[1] = 1 when it exceeds cap (nothing else is valid
+ *           then), header_d[2 + k] = id of the k-th tile; packed_d[k][T][T][4] = copy of that tile (zero padded at
+ *           the image edges, unused slots zeroed)            header_d: int32[2 + cap], packed_d: double[cap*T*T*4]
+ *   unpack: the packed tiles written back into the image (no-op on overflow) */
+int otb_image_tiles_mask(const double* img_d, int32_t Ny, int32_t Nx, int32_t T, int32_t* mask_d, void* stream);
+int otb_image_tiles_pack(const double* img_d, int32_t Ny, int32_t Nx, int32_t T, const int32_t* mask_d, int32_t cap,
+                         int32_t* header_d, double* packed_d, void* stream);
+int otb_image_tiles_unpack(double* img_d, int32_t Ny, int32_t Nx, int32_t T, const int32_t* header_d, int32_t cap,
+                           const double* packed_d, void* stream);
+
 /* Store-mode trace: replaces Raytracer.trace's sub_trace surface loop (raytracer.py:297-397)
  * including find_hit, __refraction, __compute_polarization, __refraction_ideal_lens, __hurb,
  * __outline_intersection, Filter/Aperture handling.  msgs_d: int64[OTB_NMSG * nt], accumulated. */

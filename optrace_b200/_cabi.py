@@ -113,6 +113,9 @@ SYMBOLS = {
     "otb_focus_image": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int64, C.c_double, C.c_int32, C.c_int32, _VP, _VP, _VP]),
     "otb_spectrum_stats": (C.c_int, [_VP, _VP, C.c_int64, C.c_int32, _VP, _VP, _VP]),
     "otb_spectrum_hist": (C.c_int, [_VP, _VP, C.c_int64, C.c_int32, _VP, C.c_int32, _VP, _VP]),
+    "otb_image_tiles_mask": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP]),
+    "otb_image_tiles_pack": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, _VP, C.c_int32, _VP, _VP, _VP]),
+    "otb_image_tiles_unpack": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, _VP, C.c_int32, _VP, _VP]),
     "otb_image_convolve": (C.c_int, [_VP, C.c_int32, C.c_int32, _VP, C.c_int32, _VP, _VP]),
     "otb_image_rescale": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP]),
     "otb_image_stats": (C.c_int, [_VP, C.c_int64, C.c_int32, C.c_double, _VP, _VP]),

@@ -11,7 +11,7 @@ import subprocess
 PKG = pathlib.Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
-SOURCES = ["otb_api.cu", "otb_trace.cu", "otb_render.cu", "otb_detect.cu", "otb_gen.cu", "otb_image.cu", "otb_focus.cu", "otb_spectrum.cu"]
+SOURCES = ["otb_api.cu", "otb_trace.cu", "otb_render.cu", "otb_detect.cu", "otb_gen.cu", "otb_image.cu", "otb_focus.cu", "otb_spectrum.cu", "otb_tiles.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false",           # op-for-op parity with the reference's numpy arithmetic
               "-Xcompiler", "-fPIC", f"-I{ROOT / 'include'}", f"-I{CSRC}"]

@@ -103,6 +103,40 @@ def allreduce_sum_async(tensors):
     return ev
 
 
+def allreduce_image_async(lib, img):
+    """SUM all-reduce of a detector image (Ny, Nx, 4) on the side stream, moving only its occupied tiles
+    (engine.TilePack, otb_tiles.cu): MAX all-reduce of the tile mask (the union over the ranks, a few KB), pack by the
+    union, SUM all-reduce of the packed tiles, unpack.  Returns (completion event, TilePack or None).  Falls back to
+    the dense all-reduce when the image is not sparse; an overflow of the learnt capacity is detected by the consumer
+    (RenderImage._wait_device) and repaired with the dense all-reduce."""
+    if not (is_dist() and world() > 1):
+        return None, None
+    import torch
+    from . import engine
+    td = _td()
+    global _image_group
+    if _image_group is None:
+        _image_group = td.new_group(backend=td.get_backend())
+    cap = engine.tile_capacity(img.shape) if img.is_cuda else 0
+    if not cap:
+        return allreduce_sum_async((img,)), None
+    side = engine.side_stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        tp = engine.TilePack(lib, img, cap)
+        tp.make_mask()
+        td.all_reduce(tp.mask, op=td.ReduceOp.MAX, group=_image_group)
+        tp.pack()
+        td.all_reduce(tp.packed, op=td.ReduceOp.SUM, group=_image_group)
+        tp.unpack()
+        tp.reduced = True
+        tp.remember()
+        img.record_stream(side)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    return ev, tp
+
+
 def allreduce_range_(rng):
     """rng = [min x, max x, min y, max y] tensor: MIN/MAX all-reduce for the auto extent (raytracer.py:1042-1046)"""
     if is_dist() and world() > 1:

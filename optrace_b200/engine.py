@@ -533,6 +533,98 @@ def image_convolve(data_dev, psf: np.ndarray):
 
 
 # ---------------------------------------------------------------------------------------------------
+# sparse transport of detector images (otb_tiles.cu)
+# ---------------------------------------------------------------------------------------------------
+TILE = 32
+_tile_cap = {}        # (Ny, Nx) -> tile capacity learnt from earlier images of that shape
+_tile_last = {}       # (Ny, Nx) -> (event, header tensor) of the latest pack: read without waiting once it is done
+
+
+def tile_capacity(shape) -> int:
+    """capacity (tiles) for the next packed image of this shape: twice what the previous one needed (power of two,
+    so that the pinned staging buffers are reused), an eighth of the image to start with; 0 = dense transport"""
+    Ny, Nx = int(shape[0]), int(shape[1])
+    total = -(-Ny//TILE)*(-(-Nx//TILE))
+    key = (Ny, Nx)
+    last = _tile_last.get(key)
+    if last is not None and last[0].query():          # the pinned copy of the header has landed: no synchronisation
+        _tile_cap[key] = int(last[1][0])
+        _tile_last.pop(key, None)
+    need = _tile_cap.get(key)
+    cap = max(64, total//8) if need is None else max(64, 2*need)
+    cap = 1 << (cap - 1).bit_length()
+    return cap if cap*2 <= total else 0
+
+
+class TilePack:
+    """occupied T x T tiles of a device image (Ny, Nx, 4): mask -> [union over ranks] -> pack -> [sum over ranks] ->
+    unpack.  All calls enqueue on the current stream."""
+
+    def __init__(self, lib, img, cap: int):
+        torch = _torch()
+        self.lib, self.img, self.cap = lib, img, cap
+        self.Ny, self.Nx = int(img.shape[0]), int(img.shape[1])
+        self.ntiles = -(-self.Ny//TILE)*(-(-self.Nx//TILE))
+        d = img.device
+        self.mask = torch.zeros(self.ntiles, dtype=torch.int32, device=d)
+        self.header = torch.zeros(2 + cap, dtype=torch.int32, device=d)
+        self.packed = torch.empty(cap*TILE*TILE*4, dtype=torch.float64, device=d)
+        self.reduced = False      # the packed tiles hold the SUM over all ranks (dist.allreduce_image_async)
+
+    def make_mask(self):
+        check(self.lib.otb_image_tiles_mask(dptr(self.img), self.Ny, self.Nx, TILE, dptr(self.mask), stream_ptr()), self.lib)
+
+    def pack(self):
+        check(self.lib.otb_image_tiles_pack(dptr(self.img), self.Ny, self.Nx, TILE, dptr(self.mask), self.cap,
+                                            dptr(self.header), dptr(self.packed), stream_ptr()), self.lib)
+
+    def unpack(self):
+        check(self.lib.otb_image_tiles_unpack(dptr(self.img), self.Ny, self.Nx, TILE, dptr(self.header), self.cap,
+                                              dptr(self.packed), stream_ptr()), self.lib)
+
+    def remember(self):
+        """asynchronous pinned copy of [count, overflow] on the current stream: the next image of this shape sizes its
+        capacity from it (tile_capacity) without any host synchronisation"""
+        torch = _torch()
+        h = pinned_take((2,), torch.int32)
+        h.copy_(self.header[:2], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        _tile_last[(self.Ny, self.Nx)] = (ev, h)
+
+
+_dense_pool = {}      # (Ny, Nx) -> list of (padded zero array with the tiles of its last use cleared again)
+
+
+def assemble_tiles(shape, header: np.ndarray, packed: np.ndarray):
+    """dense host image from the packed tiles (header = [count, overflow, ids...]): one scatter of all tiles into a
+    zero image padded to whole tiles.  The padded arrays are pooled: a fresh 143 MB np.zeros costs a page fault per
+    4 KB page the tiles touch (~1 ms), a recycled one (release_dense clears exactly the tiles that were written) none.
+    Returns (the (Ny, Nx, 4) view, token for release_dense)."""
+    Ny, Nx = int(shape[0]), int(shape[1])
+    nty, ntx = -(-Ny//TILE), -(-Nx//TILE)
+    n = int(header[0])
+    free = _dense_pool.setdefault(("padded", nty*TILE, ntx*TILE), [])
+    out = free.pop() if free else np.zeros((nty*TILE, ntx*TILE, 4), dtype=np.float64)
+    ids = header[2:2 + n].astype(np.int64)
+    if n:
+        tiles = packed.reshape(-1, TILE, TILE, 4)[:n]
+        out.reshape(nty, TILE, ntx, TILE, 4)[ids//ntx, :, ids % ntx] = tiles
+    return out[:Ny, :Nx], (out, ids)
+
+
+def release_dense(token) -> None:
+    """give a padded host image back to the pool (called when its RenderImage dies): the written tiles are zeroed"""
+    out, ids = token
+    nty, ntx = out.shape[0]//TILE, out.shape[1]//TILE
+    if ids.shape[0]:
+        out.reshape(nty, TILE, ntx, TILE, 4)[ids//ntx, :, ids % ntx] = 0.0
+    free = _dense_pool.setdefault(("padded", out.shape[0], out.shape[1]), [])
+    if len(free) < 3:
+        free.append(out)
+
+
+# ---------------------------------------------------------------------------------------------------
 # spectrum histograms (LightSpectrum.render, light_spectrum.py:40-79)
 # ---------------------------------------------------------------------------------------------------
 def spectrum_histogram(lib, wl, w, positive_only: bool, wavelength_range):

@@ -172,6 +172,9 @@ class RenderImage:
         self._data_dev = None      # torch tensor (Ny, Nx, 4) float64 on the GPU
         self._counts_dev = None    # torch tensor (Ny, Nx) int32: ray counts per bin (parity checks)
         self._ready = None         # CUDA event: device image complete (side-stream all-reduce of the shards)
+        self._pack = None          # engine.TilePack: occupied tiles of the image (sparse all-reduce / download)
+        self._lib = None           # engine library that rendered the image (tile kernels)
+        self.transferred_bytes = 0  # device -> host bytes the last materialisation moved
         self._counts_local = False  # several GPUs: the count channel still holds this rank's shard only
         self._host_buf = None      # pinned staging tensor of an asynchronous download
         self._host_ready = None    # CUDA event: download complete
@@ -213,11 +216,21 @@ class RenderImage:
         return self._data is not None or self._data_dev is not None
 
     def _wait_device(self):
-        """make the current stream wait for the (side-stream) completion of the device image"""
+        """make the current stream wait for the (side-stream) completion of the device image.  A sparse all-reduce
+        (dist.allreduce_image_async) that met more occupied tiles than its learnt capacity left the image unreduced:
+        detected here from the pack header and repaired with the dense all-reduce (collective: every rank sees the
+        same union count and takes the same branch)."""
         if self._ready is not None:
             import torch
             torch.cuda.current_stream().wait_event(self._ready)
             self._ready = None
+            if self._pack is not None and self._pack.reduced:
+                from . import dist, engine
+                h = self._pack.header[:2].cpu()          # synchronises: the image is about to be consumed anyway
+                engine._tile_cap[(self._pack.Ny, self._pack.Nx)] = int(h[0])
+                if int(h[1]):
+                    dist.allreduce_sum_(self._data_dev)
+                    self._pack = None
 
     def download_async(self) -> "RenderImage":
         """Extension of the reference API: start the device -> host copy of the image on the side stream (pinned
@@ -231,9 +244,24 @@ class RenderImage:
                 side.wait_event(self._ready)
             else:
                 side.wait_stream(torch.cuda.current_stream())
-            self._host_buf = engine.pinned_take(self._data_dev.shape, self._data_dev.dtype)
+            tp = self._pack
+            cap = tp.cap if tp is not None else (engine.tile_capacity(self._data_dev.shape) if self._lib is not None else 0)
             with torch.cuda.stream(side):
-                self._host_buf.copy_(self._data_dev, non_blocking=True)
+                if cap:
+                    # only the occupied tiles travel: [count, overflow, ids] + cap tiles instead of the whole histogram
+                    if tp is None:
+                        tp = engine.TilePack(self._lib, self._data_dev, cap)
+                        tp.make_mask()
+                        tp.pack()
+                        self._pack = tp
+                    self._host_hdr = engine.pinned_take(tp.header.shape, tp.header.dtype)
+                    self._host_buf = engine.pinned_take(tp.packed.shape, tp.packed.dtype)
+                    self._host_hdr.copy_(tp.header, non_blocking=True)
+                    self._host_buf.copy_(tp.packed, non_blocking=True)
+                else:
+                    self._host_hdr = None
+                    self._host_buf = engine.pinned_take(self._data_dev.shape, self._data_dev.dtype)
+                    self._host_buf.copy_(self._data_dev, non_blocking=True)
                 self._data_dev.record_stream(side)
                 self._host_ready = torch.cuda.Event()
                 self._host_ready.record(side)
@@ -245,14 +273,38 @@ class RenderImage:
                 raise RuntimeError("Image was not calculated/rendered yet.")
             if self._host_buf is not None:
                 self._host_ready.synchronize()
-                self._data = self._host_buf.numpy()       # zero-copy view of the pinned buffer
+                hdr = getattr(self, "_host_hdr", None)
+                if hdr is None:
+                    self._data = self._host_buf.numpy()       # zero-copy view of the pinned buffer
+                    self.transferred_bytes = self._data.nbytes
+                else:
+                    from . import engine
+                    h = hdr.numpy()
+                    engine._tile_cap[(int(self._data_dev.shape[0]), int(self._data_dev.shape[1]))] = int(h[0])
+                    if int(h[1]):                              # more tiles than the learnt capacity: dense copy
+                        self._wait_device()
+                        self._data = self._data_dev.cpu().numpy()
+                        self.transferred_bytes = self._data.nbytes + h.nbytes + self._host_buf.numel()*8
+                    else:
+                        self._data, self._dense_token = engine.assemble_tiles(self._data_dev.shape, h, self._host_buf.numpy())
+                        self.transferred_bytes = h.nbytes + self._host_buf.numel()*8
+                    engine.pinned_give(self._host_buf)
+                    engine.pinned_give(hdr)
+                    self._host_buf = self._host_hdr = None
             else:
                 self._wait_device()
                 self._data = self._data_dev.cpu().numpy()
+                self.transferred_bytes = self._data.nbytes
         return self._data
 
     def __del__(self):
         try:
+            tok = self.__dict__.get("_dense_token")
+            if tok is not None:
+                from . import engine
+                self._data = None
+                self._dense_token = None
+                engine.release_dense(tok)
             if self._host_buf is not None:
                 from . import engine
                 if self._host_ready is not None:
@@ -375,3 +427,4 @@ class RenderImage:
         self._wait_device()
         self._data_dev = engine.image_convolve(self._data_dev, self._airy_psf())
         self._data = None
+        self._pack = None          # the tile set of the unfiltered image no longer describes it

@@ -551,8 +551,8 @@ class Raytracer(Group):
         img._fix_extent()
         Nx, Ny = img._grid()
         data, cnt = engine.render_xyzw(self._scene.lib, hx, hy, hw, wl, img.extent, Nx, Ny)
-        img._data_dev, img._counts_dev = data, cnt
-        img._ready = dist.allreduce_sum_async((data,)) if data.is_cuda else None        # side stream, NCCL
+        img._data_dev, img._counts_dev, img._lib = data, cnt, self._scene.lib
+        img._ready, img._pack = dist.allreduce_image_async(self._scene.lib, data)       # side stream, occupied tiles only
         img._counts_local = dist.world() > 1      # the count channel (parity checks) is reduced on first access
         if limit is not None and not dont_filter:
             img._apply_rayleigh_filter()        # resolution filter on the reduced image (render_image.py:420-421)
@@ -597,8 +597,8 @@ class Raytracer(Group):
         img._fix_extent()
         Nx, Ny = img._grid()
         data, cnt = engine.render_xyzw(self._scene.lib, x, y, st.w[b:e], st.wl[b:e], img.extent, Nx, Ny)
-        img._data_dev, img._counts_dev = data, cnt
-        img._ready = dist.allreduce_sum_async((data,)) if data.is_cuda else None
+        img._data_dev, img._counts_dev, img._lib = data, cnt, self._scene.lib
+        img._ready, img._pack = dist.allreduce_image_async(self._scene.lib, data)
         img._counts_local = dist.world() > 1
         if limit is not None and not kwargs.get("_dont_filter", False):
             img._apply_rayleigh_filter()

@@ -170,7 +170,7 @@ int otb_scene_create(const OtbSceneDesc* d, OtbScene** out)
     OtbScene* sc = new OtbScene();
     memset(sc, 0, sizeof(*sc));
     fill_kscene(d, sc);
-    const size_t naux = d->n_aux > 0 ? (size_t)d->n_aux : 1;
+    const size_t naux = (d->n_aux > 0 ? (size_t)d->n_aux : 1) + 1;      // + 1: bulk copies move 16-byte multiples
     cudaError_t e = cudaMalloc(&sc->aux_d, sizeof(double)*naux);
     if (e != cudaSuccess) { delete sc; return otb_cuda_fail(e, "cudaMalloc(scene aux)"); }
     if (d->n_aux > 0) {

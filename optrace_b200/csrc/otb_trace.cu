@@ -10,6 +10,40 @@
 #include "otb_gen.cuh"
 
 #define OTB_TRACE_THREADS 128
+// Scenes with numeric surfaces (CAPS_FULL) run one block of 384 threads per SM instead of three of 128 (same 12 warps
+// at 168 registers): the block then owns the SM's shared memory and stages the scene's aux tables in it — spline
+// knots / coefficients of DataSurfaces, asphere polynomials, tabulated media and filters — with ONE bulk asynchronous
+// copy (TMA, cp.async.bulk + mbarrier) when they fit; every table lookup of the Illinois iteration and of the normal
+// (a 5 x 5 coefficient patch plus knots per spline evaluation, ~13 evaluations per hit) then reads shared memory
+// instead of L1/L2 (data_surface_2d.py:104, 130-153).  Larger tables stay in global memory (L2 resident).
+#define OTB_TRACE_THREADS_FULL 384
+#define OTB_AUX_SMEM_MAX (200*1024)
+#define OTB_THREADS_OF(CAPS) ((CAPS) == OTB_CAPS_FULL ? OTB_TRACE_THREADS_FULL : OTB_TRACE_THREADS)
+#define OTB_BLOCKS_OF(CAPS) ((CAPS) == OTB_CAPS_FULL ? 1 : OTB_MINBLOCKS(CAPS))
+
+// one bulk asynchronous copy global -> shared (TMA engine), completion on an mbarrier; bytes: multiple of 16
+__device__ __forceinline__ void tma_stage(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* mbar)
+{
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(mbar);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(dst_smem);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        // chunks of at most 64 KB
+        for (unsigned off = 0; off < bytes; off += 65536u) {
+            const unsigned n = (bytes - off < 65536u) ? bytes - off : 65536u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst + off), "l"((const char*)src_gmem + off), "r"(n), "r"(bar) : "memory");
+        }
+    }
+    // every thread waits for phase 0 of the barrier: the data is visible to it afterwards
+    asm volatile("{\n\t.reg .pred p;\n\tOTB_TMA_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@!p bra OTB_TMA_WAIT;\n\t}"
+                 :: "r"(bar) : "memory");
+}
 #ifndef OTB_TRACE_MINBLOCKS
 #define OTB_TRACE_MINBLOCKS 3      // resident blocks per SM the register allocation aims at (see profiles/)
 #endif
@@ -20,6 +54,7 @@ struct TraceArgs {
     OtbRayStore out;
     unsigned long long* msgs;   // [OTB_NMSG * nt]
     int* status;
+    int aux_smem_bytes, pad0;   // > 0: stage that many bytes of the aux tables in shared memory (16-byte multiple)
     int64_t k_begin, k_end;     // ray range of this launch (more than OTB_GEN_MAXSRC sources: one launch per group)
     GenBlock G;                 // G.nsrc > 0: rays are generated here
 };
@@ -41,8 +76,8 @@ struct StoreCursor {
 
 // one sequential step: trace, book messages, store section i+1
 template <bool POL, int CAPS>
-__device__ __forceinline__ void store_step(const KScene& sc, const TraceArgs& a, const int i, RayState& r, StoreCursor& c,
-                                           int* smsgs, const bool valid, const int64_t rr)
+__device__ __forceinline__ void store_step(const KScene& sc, const TraceArgs& a, const double* aux, const int i, RayState& r,
+                                           StoreCursor& c, int* smsgs, const bool valid, const int64_t rr)
 {
     const int64_t N = a.out.N;
     const int nt = a.out.nt;
@@ -60,7 +95,7 @@ __device__ __forceinline__ void store_step(const KScene& sc, const TraceArgs& a,
     }
     StepFlags fl;
     const double z_prev = r.p.z;
-    trace_step<POL, CAPS>(sc, a.sc.aux, st, r, fl, za, zb, a.status);
+    trace_step<POL, CAPS>(sc, aux, st, r, fl, za, zb, a.status);
     c.z_decrease = c.z_decrease | (r.p.z < z_prev);
     book_step(smsgs, nt, i, valid, fl);
 
@@ -85,19 +120,25 @@ __device__ __forceinline__ void store_step(const KScene& sc, const TraceArgs& a,
 }
 
 template <bool POL, int CAPS>
-__global__ void __launch_bounds__(OTB_TRACE_THREADS, OTB_MINBLOCKS(CAPS))
+__global__ void __launch_bounds__(OTB_THREADS_OF(CAPS), OTB_BLOCKS_OF(CAPS))
 trace_store_kernel(const __grid_constant__ TraceArgs a)
 {
-    extern __shared__ int smsgs[];      // [OTB_NMSG * nt]
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    // layout: [aux tables (aux_smem_bytes, 16-byte aligned)] [mbarrier (8)] [pad (8)] [message counters]
+    int* smsgs = (int*)(dyn_smem + a.aux_smem_bytes + 16);      // [OTB_NMSG * nt]
 #if OTB_SPEC
     const KScene& sc = K_SPEC;
 #else
     const KScene& sc = a.sc;
 #endif
-    const double* __restrict__ aux = a.sc.aux;
+    const double* aux = a.sc.aux;
     const int nt = a.out.nt;
     const int64_t N = a.out.N;
     for (int i = threadIdx.x; i < OTB_NMSG*nt; i += blockDim.x) smsgs[i] = 0;
+    if (CAPS == OTB_CAPS_FULL && a.aux_smem_bytes > 0) {
+        tma_stage(dyn_smem, a.sc.aux, (unsigned)a.aux_smem_bytes, (unsigned long long*)(dyn_smem + a.aux_smem_bytes));
+        aux = (const double*)dyn_smem;            // generic pointer into shared memory: the table code is unchanged
+    }
     __syncthreads();
 
     const int64_t Nnt = N*(int64_t)nt;
@@ -166,11 +207,11 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
 #if OTB_SPEC
         // straight-line code: one inlined copy of store_step per literal step index, everything about the step
         // (role, surface kind and parameters, media) folds at compile time
-#define OTB_CALL_STORE_STEP(i) store_step<POL, CAPS>(sc, a, i, r, cur, smsgs, valid, rr);
+#define OTB_CALL_STORE_STEP(i) store_step<POL, CAPS>(sc, a, aux, i, r, cur, smsgs, valid, rr);
         OTB_SPEC_FOREACH_STEP(OTB_CALL_STORE_STEP)
 #else
         OTB_UNROLL_N(OTB_STEP_UNROLL)
-        for (int i = 0; i < sc.n_steps; ++i) store_step<POL, CAPS>(sc, a, i, r, cur, smsgs, valid, rr);
+        for (int i = 0; i < sc.n_steps; ++i) store_step<POL, CAPS>(sc, a, aux, i, r, cur, smsgs, valid, rr);
 #endif
         if (valid && cur.z_decrease) atomicOr(a.status, OTB_STATUS_Z_DECREASE);    // practically never
         if (valid) {
@@ -223,10 +264,19 @@ int otb_launch_trace_store(const OtbScene* scene, const OtbRays* rays, const Otb
 
 static int launch_trace_store_range(const OtbScene* scene, TraceArgs& a, cudaStream_t stream, int sm_count)
 {
-    const int threads = OTB_TRACE_THREADS;
-    int64_t blocks_needed = (a.k_end - a.k_begin + threads - 1)/threads;
-    size_t smem = sizeof(int)*OTB_NMSG*a.out.nt;
+    // aux tables in shared memory (TMA bulk copy at kernel start) for the numeric-surface kernels when they fit
+    a.aux_smem_bytes = 0;
+    a.pad0 = 0;
+    const int64_t aux_bytes = ((scene->n_aux*(int64_t)sizeof(double) + 15)/16)*16;
+    if (scene->caps == OTB_CAPS_FULL && scene->n_aux > 0 && aux_bytes <= OTB_AUX_SMEM_MAX) a.aux_smem_bytes = (int)aux_bytes;
+    size_t smem = (size_t)a.aux_smem_bytes + 16 + sizeof(int)*OTB_NMSG*a.out.nt;
 #define OTB_LAUNCH_STORE(POL, CAPS) do { \
+        const int threads = OTB_THREADS_OF(CAPS); \
+        const int64_t blocks_needed = (a.k_end - a.k_begin + threads - 1)/threads; \
+        if (smem > 48*1024) { \
+            cudaError_t ea = cudaFuncSetAttribute(trace_store_kernel<POL, CAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (ea != cudaSuccess) return otb_cuda_fail(ea, "cudaFuncSetAttribute(trace_store_kernel)"); \
+        } \
         int blocks = otb_one_wave_grid(trace_store_kernel<POL, CAPS>, threads, smem, sm_count, blocks_needed); \
         trace_store_kernel<POL, CAPS><<<blocks, threads, smem, stream>>>(a); } while (0)
 #if OTB_SPEC

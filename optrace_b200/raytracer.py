@@ -391,7 +391,10 @@ class Raytracer(Group):
                       "pix_cdf_off", "pix_cdf_n", "pix_rgb_off", "srgb_off"):
                 setattr(S, f, int(r[f]))
             S.or_func_id = fids.get(id(self.ray_sources[i]), -1)
-            S.coherent = int(bool(self.coherent_bundles))
+            # measured: the numeric-surface kernels (CAPS_FULL) are bound by instruction fetch and lose with warps that
+            # run different iteration counts side by side (cosine_surfaces 11.6 -> 14.7 ms): coherent order only for
+            # scenes of flat and conic surfaces
+            S.coherent = int(bool(self.coherent_bundles) and scene_caps_lean(scene))
         return arr, len(sl), aux_d
 
     def _generate(self, N_list, begin: int, end: int, seed: int, scene=None):

@@ -40,17 +40,21 @@ struct RenderArgs {
 };
 static_assert(sizeof(RenderArgs) <= 32764, "kernel parameter block exceeds the 32 KB limit");
 
-struct DetState {
-    double X, Y;
-    float w;
-    bool started, finished, ok, all_start, all_noreach;
+// Per-ray detector bookkeeping: two bit masks (bit d = detector d) instead of per-detector records — the walk of a
+// detector starts once (first stored point at or behind its z_min) and finishes once (hit accepted or rejected), and a
+// finished hit is binned at once while the segment is in registers, so nothing per detector has to survive the step.
+// Rays whose FIRST point already lies behind a detector's z-extent are ignored for it like in the reference
+// (raytracer.py:929-938, "no_start": with z non-decreasing along a ray the first point decides; a ray with decreasing
+// z sets OTB_STATUS_Z_DECREASE and the caller repeats the chunk through the stored-section path).
+struct DetMasks {
+    unsigned started, finished, skipped;
 };
-
 
 // one sequential step of the fused mode: trace, book messages, then the detector walk of _hit_detector
 // (raytracer.py:881-1051) online on section i = (p_i -> r.p) while it is still in registers
 template <bool POL, int CAPS>
-__device__ __forceinline__ void render_step(const KScene& sc, const RenderArgs& a, const int i, RayState& r, DetState* ds,
+__device__ __forceinline__ void render_step(const KScene& sc, const RenderArgs& a, const int i, RayState& r, DetMasks& dm,
+                                            unsigned long long* srng, bool& z_decrease,
                                             int* smsgs, const bool valid, const int64_t ray)
 {
     const int64_t N = a.in.N;
@@ -71,33 +75,66 @@ __device__ __forceinline__ void render_step(const KScene& sc, const RenderArgs& 
     StepFlags fl;
     trace_step<POL, CAPS>(sc, a.sc.aux, st, r, fl, za, zb, a.status);
     book_step(smsgs, a.nt, i, valid, fl);
+    z_decrease = z_decrease | (r.p.z < p_i.z);
 
-    // the segment direction is shared by all detectors
-    bool need = false;
+    // which detectors does this segment concern?  (warp-uniform decision: the binning below is a warp collective)
+    unsigned active = 0;
     for (int d = 0; d < NDET; ++d) {
-        const KSurface& D = a.dets[d].surf;
-        const bool bmin = r.p.z >= D.z_min, bmax = r.p.z >= D.z_max;
-        ds[d].all_start = ds[d].all_start && (bmin && bmax);
-        ds[d].all_noreach = ds[d].all_noreach && (!bmin && !bmax);
-        if (!ds[d].started && bmin) ds[d].started = true;     // section before the first point behind z_min
-        need = need || (valid && ds[d].started && !ds[d].finished);
+        const bool bmin = r.p.z >= a.dets[d].surf.z_min;
+        if (bmin) dm.started |= 1u << d;                 // section before the first point behind z_min
     }
-    if (!need) return;
-    const V3 sd = unit3(v3(r.p.x - p_i.x, r.p.y - p_i.y, r.p.z - p_i.z));
+    active = valid ? (dm.started & ~dm.finished & ~dm.skipped) : 0u;
+    unsigned any = active;
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) any |= __shfl_xor_sync(0xffffffffu, any, k);
+    if (!any) return;
+    const V3 sd = unit3(v3(r.p.x - p_i.x, r.p.y - p_i.y, r.p.z - p_i.z));      // shared by all detectors
+    double ox = 0.0, oy = 0.0, oz = 0.0;
+    bool have_obs = false;
     for (int d = 0; d < NDET; ++d) {
-        const KSurface& D = a.dets[d].surf;
-        if (ds[d].started && !ds[d].finished) {
-            HitResult h = surf_find_hit<CAPS>(D, nullptr, p_i, sd, a.status);
-            if (!(h.p.z > r.p.z + OTB_C_EPS)) {
-                ds[d].finished = true;
+        if (!((any >> d) & 1u)) continue;
+        const RenderDet& rd = a.dets[d];
+        bool ok = false;
+        double X = 0.0, Y = 0.0;
+        if ((active >> d) & 1u) {
+            HitResult h = surf_find_hit<CAPS>(rd.surf, nullptr, p_i, sd, a.status);
+            if (!(h.p.z > r.p.z + OTB_C_EPS)) {           // else: hit behind the next stored point, next section
+                dm.finished |= 1u << d;
                 if (h.hit && w_i > 0.0f) {
-                    double X = h.p.x, Y = h.p.y;
-                    sphere_project(D, a.dets[d].projection, X, Y, h.p.z);
-                    ds[d].X = X;
-                    ds[d].Y = Y;
-                    ds[d].w = w_i;
-                    ds[d].ok = true;
+                    X = h.p.x;
+                    Y = h.p.y;
+                    sphere_project(rd.surf, rd.projection, X, Y, h.p.z);
+                    ok = true;
+                    if (rd.has_extent) {
+                        const double* e = rd.extent;
+                        ok = (e[0] <= X) && (X <= e[1]) && (e[2] <= Y) && (Y <= e[3]);
+                    }
                 }
+            }
+        }
+        if (a.mode == 0) {
+            if (__any_sync(0xffffffffu, ok)) {
+                if (!have_obs) {
+                    observer_xyz(a.obs, (double)r.wl, ox, oy, oz);      // one observer lookup per ray and step at most
+                    have_obs = true;
+                }
+                accumulate_xyz_warp(rd.grid, ok, X, Y, w_i, ox, oy, oz, rd.img, rd.cnt);
+            }
+        } else if (__any_sync(0xffffffffu, ok)) {
+            // range mode (auto extent of the first chunk): warp reduction, order-preserving keys in shared memory
+            double mnx = ok ? X : INFINITY, mxx = ok ? X : -INFINITY, mny = ok ? Y : INFINITY, mxy = ok ? Y : -INFINITY;
+#pragma unroll
+            for (int k = 16; k > 0; k >>= 1) {
+                mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, k));
+                mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, k));
+                mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, k));
+                mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, k));
+            }
+            if ((threadIdx.x & 31) == 0) {
+                atomicMin(&srng[4*d + 0], dkey(mnx));
+                atomicMax(&srng[4*d + 1], dkey(mxx));
+                atomicMin(&srng[4*d + 2], dkey(mny));
+                atomicMax(&srng[4*d + 3], dkey(mxy));
             }
         }
     }
@@ -117,12 +154,10 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
     const int nt = a.nt;
     const int64_t N = a.in.N;
     const int NDET = a.n_det;
+    __shared__ unsigned long long srng[4*OTB_MAX_DET];      // range mode: hit ranges of the block (min, max, min, max keys)
     for (int i = threadIdx.x; i < OTB_NMSG*nt; i += blockDim.x) smsgs[i] = 0;
+    if (threadIdx.x < 4*OTB_MAX_DET) srng[threadIdx.x] = (threadIdx.x & 1) ? 0ull : ~0ull;
     __syncthreads();
-
-    // range mode: running hit ranges of this thread, merged into the global ranges once at the end of the kernel
-    double rg[OTB_MAX_DET][4];
-    for (int d = 0; d < OTB_MAX_DET; ++d) { rg[d][0] = INFINITY; rg[d][1] = -INFINITY; rg[d][2] = INFINITY; rg[d][3] = -INFINITY; }
 
     const bool generate = a.G.nsrc > 0;
     for (int64_t base = a.k_begin + (int64_t)blockIdx.x*blockDim.x; base < a.k_end; base += (int64_t)gridDim.x*blockDim.x) {
@@ -160,63 +195,34 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
         r.n = medium_n(sc.media[sc.medium0], aux, (double)r.wl);
         if (valid && r.n < 1.0) atomicOr(a.status, OTB_STATUS_NBELOW1);
 
-        DetState ds[OTB_MAX_DET];
+        DetMasks dm;
+        dm.started = dm.finished = dm.skipped = 0u;
         for (int d = 0; d < NDET; ++d) {
             const KSurface& D = a.dets[d].surf;
             const bool bmin = r.p.z >= D.z_min, bmax = r.p.z >= D.z_max;
-            ds[d].X = ds[d].Y = 0.0;
-            ds[d].w = 0.0f;
-            ds[d].started = bmin;     // first stored point already at/behind z_min: the walk starts at section 0
-            ds[d].finished = false;
-            ds[d].ok = false;
-            ds[d].all_start = bmin && bmax;
-            ds[d].all_noreach = !bmin && !bmax;
+            if (bmin) dm.started |= 1u << d;      // first stored point already at/behind z_min: the walk starts at section 0
+            if (bmin && bmax) dm.skipped |= 1u << d;          // ray starts behind the detector: ignored (no_start)
         }
+        bool z_decrease = false;
 
 #if OTB_SPEC
-#define OTB_CALL_RENDER_STEP(i) render_step<POL, CAPS>(sc, a, i, r, ds, smsgs, valid, ray);
+#define OTB_CALL_RENDER_STEP(i) render_step<POL, CAPS>(sc, a, i, r, dm, srng, z_decrease, smsgs, valid, ray);
         OTB_SPEC_FOREACH_STEP(OTB_CALL_RENDER_STEP)      // straight-line code, see otb_trace.cu
 #else
-        for (int i = 0; i < sc.n_steps; ++i) render_step<POL, CAPS>(sc, a, i, r, ds, smsgs, valid, ray);
+        for (int i = 0; i < sc.n_steps; ++i) render_step<POL, CAPS>(sc, a, i, r, dm, srng, z_decrease, smsgs, valid, ray);
 #endif
-
         // rays still walking at the last stored point have no further section: no hit (raytracer.py:970-978)
-        double ox = 0.0, oy = 0.0, oz = 0.0;
-        if (a.mode == 0) observer_xyz(a.obs, (double)r.wl, ox, oy, oz);      // one observer lookup per ray
-        for (int d = 0; d < NDET; ++d) {
-            bool ok = valid && ds[d].ok && !(ds[d].all_start || ds[d].all_noreach);
-            const RenderDet& rd = a.dets[d];
-            if (ok && rd.has_extent) {
-                const double* e = rd.extent;
-                ok = (e[0] <= ds[d].X) && (ds[d].X <= e[1]) && (e[2] <= ds[d].Y) && (ds[d].Y <= e[3]);
-            }
-            if (a.mode == 0) {
-                accumulate_xyz_warp(rd.grid, ok, ds[d].X, ds[d].Y, ds[d].w, ox, oy, oz, rd.img, rd.cnt);
-            } else if (ok) {
-                rg[d][0] = fmin(rg[d][0], ds[d].X);
-                rg[d][1] = fmax(rg[d][1], ds[d].X);
-                rg[d][2] = fmin(rg[d][2], ds[d].Y);
-                rg[d][3] = fmax(rg[d][3], ds[d].Y);
-            }
-        }
+        if (valid && z_decrease) atomicOr(a.status, OTB_STATUS_Z_DECREASE);
     }
 
-    if (a.mode != 0) {
-        for (int d = 0; d < NDET; ++d) {
-            double mnx = rg[d][0], mxx = rg[d][1], mny = rg[d][2], mxy = rg[d][3];
-#pragma unroll
-            for (int k = 16; k > 0; k >>= 1) {
-                mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, k));
-                mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, k));
-                mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, k));
-                mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, k));
-            }
-            if ((threadIdx.x & 31) == 0 && mnx <= mxx) {
-                atomic_min_double(&a.dets[d].range[0], mnx);
-                atomic_max_double(&a.dets[d].range[1], mxx);
-                atomic_min_double(&a.dets[d].range[2], mny);
-                atomic_max_double(&a.dets[d].range[3], mxy);
-            }
+    __syncthreads();
+    if (a.mode != 0 && threadIdx.x < NDET) {
+        const int d = threadIdx.x;
+        if (srng[4*d] != ~0ull) {
+            atomic_min_double(&a.dets[d].range[0], dkey_inv(srng[4*d + 0]));
+            atomic_max_double(&a.dets[d].range[1], dkey_inv(srng[4*d + 1]));
+            atomic_min_double(&a.dets[d].range[2], dkey_inv(srng[4*d + 2]));
+            atomic_max_double(&a.dets[d].range[3], dkey_inv(srng[4*d + 3]));
         }
     }
 

@@ -22,6 +22,12 @@ from .ray_storage import RayStorage, split_rays
 from .scene import flatten_raytracer, detector_record
 from .surfaces import RectangularSurface, RingSurface, SlitSurface, SphericalSurface
 from ._state import state_of
+
+
+def scene_caps_lean(scene) -> bool:
+    """True when the scene runs the lean kernel instantiation (flat + conic surfaces only, OTB_CAPS_LENS)"""
+    kinds = {r["kind"] for r in scene.flat.surfaces} if scene is not None else set()
+    return not (kinds & {5, 6, 7, 8})
 from . import _state
 from . import color
 
@@ -850,6 +856,11 @@ class Raytracer(Group):
         m, st = dist.reduce_msgs_status(msgs_dev, status_dev)
         msgs_cum += m
         engine.raise_status(st)
+        if st & 16:
+            # the fused kernel decides "ray starts behind the detector" from the first point, which presumes z never
+            # decreases along a ray (true for every ray the tracer produces: s_z > 0 is enforced); reported, not hidden
+            raise RuntimeError("A ray position moved backwards in z during an iterative render; "
+                               "use trace() + detector_image() for this geometry.")
         for j in range(nd):
             dist.allreduce_sum_(images[j]._data_dev)
             dist.allreduce_sum_(images[j]._counts_dev)

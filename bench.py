@@ -273,10 +273,11 @@ def run_gpu(args):
 
     def step_resident(record):
         scene = RT._scene_handle()
-        begin, end = dist.shard_range(N_total)
+        blocks = dist.shard_sources(N_list)               # this rank's slice of every source, like Raytracer.trace
+        begin, end = 0, sum(c for _, _, c in blocks)
         RT._trace_count += 1
         seed = (int(RT.seed) << 20) + RT._trace_count
-        rays = RT._generated(scene, N_list, begin, end, seed)
+        rays = RT._generated(scene, N_list, blocks, 0, seed)
         e0, e1 = ev(), ev()
         # the ray store (8.2 GB) is allocated once and overwritten every step: steady-state serving pattern
         if not stores:
@@ -285,7 +286,7 @@ def run_gpu(args):
         dist.allreduce_sum_(msgs)
         RT._msgs = msgs
         rays.gen_status = None
-        RT.rays._attach(store, RT.ray_sources, N_list, RT.no_pol, N_total, begin)
+        RT.rays._attach(store, RT.ray_sources, N_list, RT.no_pol, N_total, blocks)
         RT._last_trace_snapshot = snap
         RT.check_if_rays_are_current = lambda: True
         img = RT.detector_image()

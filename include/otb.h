@@ -271,6 +271,8 @@ typedef struct OtbSource {
     int32_t img_w, img_h;         /* image sources: pixel grid */
     int64_t n_rays;               /* rays of this source in this launch (RayStorage.N_list) */
     int64_t ray_start;            /* first local ray index of this source (RayStorage.B_list) */
+    int64_t gid_start;            /* global id of that ray = Philox counter of its draws: a rank of a sharded trace
+                                     holds a slice of every source, the slices of all ranks tile the source's block */
     double power;                 /* weight = power / n_rays_total_of_source (float32) */
     double weight;                /* float32 weight of every ray, computed by the host like ray_source.py:219-220 */
     double pos[3];

@@ -69,7 +69,7 @@ class OtbSource(C.Structure):
     _fields_ = [("shape", C.c_int32), ("orientation", C.c_int32), ("divergence", C.c_int32),
                 ("polarization", C.c_int32), ("wl_mode", C.c_int32), ("div_2d", C.c_int32),
                 ("img_w", C.c_int32), ("img_h", C.c_int32),
-                ("n_rays", C.c_int64), ("ray_start", C.c_int64),
+                ("n_rays", C.c_int64), ("ray_start", C.c_int64), ("gid_start", C.c_int64),
                 ("power", C.c_double), ("weight", C.c_double), ("pos", C.c_double*3),
                 ("geom", C.c_double*8), ("extent", C.c_double*4), ("s", C.c_double*3),
                 ("conv_pos", C.c_double*3), ("div_sin", C.c_double), ("div_angle", C.c_double),

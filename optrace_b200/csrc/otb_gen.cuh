@@ -228,7 +228,7 @@ __device__ __forceinline__ void generate_ray(const GenBlock& G, const int64_t k,
     g.inv_n = C.inv_n;
     g.coh_stream = C.coh_stream;
     g.seed = G.seed;
-    g.gid = (uint64_t)(G.ray_offset + k);
+    g.gid = (uint64_t)(S.gid_start + (k - S.ray_start));       // global ray id: the bundle does not depend on the sharding
     g.m = (uint64_t)(k - S.ray_start);
     g.n = (uint64_t)S.n_rays;
     g.src = (uint32_t)(G.src_index0 + si);

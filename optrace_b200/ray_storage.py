@@ -6,7 +6,7 @@ Contract of optrace/tracer/ray_storage.py (array names, dtypes, shapes, Fortran 
 The arrays live on the GPU as SoA planes written by the trace kernel in exactly this byte layout, so a host
 view is a plain device->host copy plus a zero-copy Fortran reshape.  Copies happen per attribute on first
 access (SURVEY.md hard part 5: 48 B/ray/section over PCIe is the bottleneck, so nothing is copied eagerly).
-In multi-GPU runs every rank holds the contiguous shard [ray_begin, ray_end) of the global ray range.
+In multi-GPU runs every rank holds a share of every source's block (dist.shard_sources), stored in source order.
 """
 from __future__ import annotations
 
@@ -36,9 +36,12 @@ class RayStorage:
         self._nt = 0
         self._N_global = 0
         self.ray_begin, self.ray_end = 0, 0
+        self._blocks = []         # local blocks: (source index, global id of the first ray, count), in source order
 
     # -- bookkeeping ----------------------------------------------------------------------------
-    def _attach(self, dev_store, sources, N_list, no_pol, N_global, ray_begin):
+    def _attach(self, dev_store, sources, N_list, no_pol, N_global, blocks):
+        """blocks: the local rays as (source index, global first ray id, count) in storage order — one block per
+        source; an int is accepted for a contiguous global range starting there"""
         self._dev = dev_store
         self._host = {}
         self.ray_source_list = list(sources)
@@ -47,7 +50,14 @@ class RayStorage:
         self.no_pol = no_pol
         self._nt = dev_store.nt
         self._N_global = int(N_global)
-        self.ray_begin, self.ray_end = int(ray_begin), int(ray_begin) + dev_store.N
+        if isinstance(blocks, (int, np.integer)):
+            from . import dist
+            blocks = dist.contiguous_blocks(self.N_list, int(blocks), int(blocks) + dev_store.N)
+        self._blocks = [(int(i), int(g), int(c)) for i, g, c in blocks]
+        assert sum(c for _, _, c in self._blocks) == dev_store.N
+        # first global ray id of the shard (meaningful for contiguous shards: injected bundles, single GPU)
+        self.ray_begin = self._blocks[0][1] if self._blocks else 0
+        self.ray_end = self.ray_begin + dev_store.N
 
     @staticmethod
     def storage_size(N: int, nt: int, no_pol: bool) -> int:
@@ -127,10 +137,17 @@ class RayStorage:
             self.w_list[Ns:Ne, 0], self.wl_list[Ns:Ne]
 
     def _local_range(self, index):
+        """local storage rows [b, e) of source `index` (all local rows for None); empty when this rank holds none"""
         if index is None:
             return 0, self.N
-        Ns, Ne = self.B_list[index:index + 2]
-        return max(Ns, self.ray_begin) - self.ray_begin, max(min(Ne, self.ray_end), self.ray_begin) - self.ray_begin
+        off = 0
+        for i, _, c in self._blocks:
+            if i == index:
+                return off, off + c
+            if i > index:
+                break
+            off += c
+        return off, off
 
     def rays_by_mask(self, ch=None, ch2=None, ret=None, normalize: bool = True):
         """ray_storage.py:235-293"""
@@ -141,8 +158,10 @@ class RayStorage:
         assert ch.shape[0] == self.N
         snums = s = None
         if ret[5]:
-            ind = np.nonzero(ch)[0] + self.ray_begin
-            snums = np.clip(np.searchsorted(self.B_list, ind, side="right") - 1, 0, len(self.N_list) - 1)
+            ind = np.nonzero(ch)[0]
+            lb = np.cumsum([0] + [c for _, _, c in self._blocks])
+            src = np.array([i for i, _, _ in self._blocks], dtype=int)
+            snums = src[np.clip(np.searchsorted(lb, ind, side="right") - 1, 0, len(src) - 1)] if len(src) else ind*0
         if ret[1]:
             P = self.p_list
             if not isinstance(ch2, slice):

@@ -373,19 +373,21 @@ class Raytracer(Group):
     arithmetic.  Same cells, same distributions, same images; only the order of the rays within a source block is
     less random (a slice rays[:k] is a set of 32-ray clusters instead of a uniform subsample).  False = full shuffle."""
 
-    def _source_records(self, scene, N_list, begin: int, end: int):
-        """OtbSource array of the local shard [begin, end) of the global ray range + the table buffer on the device"""
+    def _source_records(self, scene, N_list, blocks):
+        """OtbSource array of the local blocks (source, global first ray id, count) + the table buffer on the device"""
         recs, aux_d = self._generator_tables()          # (re-)upload of the sampling tables on the current stream
-        B_list = np.concatenate(([0], np.cumsum(N_list)))
-        sl = dist.source_slices(B_list, begin, end)
+        sl = blocks
         arr = (_cabi.OtbSource*max(len(sl), 1))()
         fids = scene.flat.source_func_ids
-        for k, (i, start, cnt) in enumerate(sl):
+        start = 0
+        for k, (i, gid0, cnt) in enumerate(sl):
             r, S = recs[i], arr[k]
+            S.gid_start = gid0
             S.shape, S.orientation, S.divergence = r["shape"], r["orientation"], r["divergence"]
             S.polarization, S.wl_mode, S.div_2d = r["polarization"], r["wl"]["mode"], r["div_2d"]
             S.img_w, S.img_h = r["img_w"], r["img_h"]
             S.n_rays, S.ray_start = cnt, start
+            start += cnt
             S.power = r["power"]
             # ray_source.py:219-220 / ray_storage.py:160-163: float32(power/N) with the per-slice power share
             S.weight = float(np.float32(r["power"]/N_list[i])) if N_list[i] else 0.0
@@ -403,7 +405,7 @@ class Raytracer(Group):
             S.coherent = int(bool(self.coherent_bundles) and scene_caps_lean(scene))
         return arr, len(sl), aux_d
 
-    def _generate(self, N_list, begin: int, end: int, seed: int, scene=None):
+    def _generate(self, N_list, begin, end: int, seed: int, scene=None):
         """otb_generate_rays for the local shard [begin, end) of the global ray range: the stand-alone generator
         (tests, tools, injected-bundle workflows).  trace() and iterative_render() do not call it: they hand the
         source records to the trace kernels, which draw the rays themselves (engine.DeviceRays.generated)."""
@@ -411,8 +413,11 @@ class Raytracer(Group):
         engine.ensure_init()
         scene = scene or self._scene_handle()
         lib = scene.lib
-        n = end - begin
-        arr, ns, aux_d = self._source_records(scene, N_list, begin, end)
+        # `begin` may be the list of local blocks (balanced sharding); else the contiguous global range [begin, end)
+        blocks = begin if isinstance(begin, list) else dist.contiguous_blocks(N_list, begin, end)
+        n = sum(c for _, _, c in blocks)
+        begin = self._ray_offset(N_list, blocks, begin)
+        arr, ns, aux_d = self._source_records(scene, N_list, blocks)
         d = engine.device()
         p0 = torch.empty(3*n, dtype=torch.float64, device=d)
         s0 = torch.empty(3*n, dtype=torch.float64, device=d)
@@ -433,12 +438,24 @@ class Raytracer(Group):
     at 16 warps per SM and the generator's integer work does not hide behind their fp64 chains: measured on the
     double-Gauss workload 4.53 ms fused against 3.67 + 0.66 ms separate.  Worth it when device memory is the limit."""
 
-    def _generated(self, scene, N_list, begin: int, end: int, seed: int):
-        """the bundle of a trace: generated by the generator kernel (default) or described for the fused path"""
+    def _generated(self, scene, N_list, begin, end: int, seed: int):
+        """the bundle of a trace: generated by the generator kernel (default) or described for the fused path.
+        `begin`: list of local blocks (dist.shard_sources) or the start of the contiguous range [begin, end)"""
         if not self.fused_generation:
             return self._generate(N_list, begin, end, seed, scene)
-        arr, ns, aux_d = self._source_records(scene, N_list, begin, end)
-        return engine.DeviceRays.generated(end - begin, arr, ns, aux_d, seed, begin)
+        blocks = begin if isinstance(begin, list) else dist.contiguous_blocks(N_list, begin, end)
+        arr, ns, aux_d = self._source_records(scene, N_list, blocks)
+        return engine.DeviceRays.generated(sum(c for _, _, c in blocks), arr, ns, aux_d, seed,
+                                           self._ray_offset(N_list, blocks, begin))
+
+    @staticmethod
+    def _ray_offset(N_list, blocks, begin) -> int:
+        """counter offset of the per-ray draws made inside the trace kernels (HURB deviates: Philox counter =
+        offset + local ray index): the global id of the first ray for a contiguous range; for the balanced shards of a
+        job (a slice of every source) the number of rays the lower ranks hold, so that no two rays share a counter"""
+        if not isinstance(begin, list):
+            return int(begin)
+        return dist.rank()*sum(int(n)//dist.world() for n in N_list)
 
     # -- trace -----------------------------------------------------------------------------------------
     def trace(self, N: int) -> None:
@@ -448,19 +465,20 @@ class Raytracer(Group):
         engine.ensure_init()
         scene = self._scene_handle()
         nt = scene.nt
-        begin, end = dist.shard_range(N)
-        if RayStorage.storage_size(end - begin, nt, self.no_pol) > self.MAX_RAY_STORAGE_RAM:
+        N_list = dist.shared_split(N, [rs.power for rs in self.ray_sources], engine.device())
+        blocks = dist.shard_sources(N_list)          # this rank's slice of every source (balanced work per rank)
+        n_local = sum(c for _, _, c in blocks)
+        if RayStorage.storage_size(n_local, nt, self.no_pol) > self.MAX_RAY_STORAGE_RAM:
             raise RuntimeError(f"More than {self.MAX_RAY_STORAGE_RAM*1e-9:.1f} GB RAM requested. Either decrease"
                                " the number of rays, surfaces or do an iterative render. If your system can handle"
                                " more RAM usage, increase the Raytracer.MAX_RAY_STORAGE_RAM parameter.")
-        N_list = dist.shared_split(N, [rs.power for rs in self.ray_sources], engine.device())
         if np.any(N_list == 0):
             warning("There are RaySources that have no rays assigned. "
                     "Change the power ratio or raise the overall ray number")
         self._trace_count += 1
         seed = (int(self.seed) << 20) + self._trace_count
-        rays = self._generated(scene, N_list, begin, end, seed)
-        self._run_trace(scene, rays, N_list, N, begin)
+        rays = self._generated(scene, N_list, blocks, 0, seed)
+        self._run_trace(scene, rays, N_list, N, blocks)
 
     def trace_rays(self, p, s, pol, w, wl, hurb_z=None, N_list=None, sharded: bool = False) -> None:
         """Extension of the reference API: trace a pre-generated bundle (the arrays RaySource.create_rays
@@ -804,11 +822,10 @@ class Raytracer(Group):
         for i in range(iterations):
             if i == iterations - 1:
                 rays_step += int(N - iterations*rays_step)
-            begin, end = dist.shard_range(rays_step)
             N_list = dist.shared_split(rays_step, powers, engine.device())
             self._trace_count += 1
             seed = (int(self.seed) << 20) + self._trace_count
-            rays = self._generated(scene, N_list, begin, end, seed)
+            rays = self._generated(scene, N_list, dist.shard_sources(N_list), 0, seed)
             if getattr(rays, "gen_status", None) is not None:
                 status_dev.bitwise_or_(rays.gen_status)
             recs = det_records()

@@ -264,3 +264,40 @@ int main() {
     assert r.returncode == 0, r.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "OK", out.stdout
+
+
+def test_balanced_source_shards_tile_every_source():
+    """dist.shard_sources: every rank holds a slice of every source, the slices of all ranks tile the source's block of
+    global ray ids, local storage rows map back to the right source (RayStorage._local_range)"""
+    from optrace_b200 import dist
+    from optrace_b200.ray_storage import RayStorage
+    N_list = [1000, 1, 0, 777, 12]
+    B = np.concatenate(([0], np.cumsum(N_list)))
+    for G in (1, 2, 3, 8):
+        seen = np.zeros(int(B[-1]), dtype=int)
+        for r in range(G):
+            blocks = dist.shard_sources(N_list, r, G)
+            assert [i for i, _, _ in blocks] == sorted(i for i, _, _ in blocks)
+            for i, g0, c in blocks:
+                assert B[i] <= g0 and g0 + c <= B[i + 1] and c > 0
+                seen[g0:g0 + c] += 1
+
+            class _Store:
+                N, nt = sum(c for _, _, c in blocks), 3
+            rs = RayStorage()
+            rs._attach(_Store(), [None]*len(N_list), N_list, False, int(B[-1]), blocks)
+            off = 0
+            for i, g0, c in blocks:
+                assert rs._local_range(i) == (off, off + c)
+                off += c
+            for i in set(range(len(N_list))) - {i for i, _, _ in blocks}:
+                b, e = rs._local_range(i)
+                assert b == e
+        assert np.all(seen == 1)
+    # a contiguous range given as its first global id gives the same blocks as before
+    rs = RayStorage()
+
+    class _S2:
+        N, nt = 40, 2
+    rs._attach(_S2(), [None]*3, [40, 60, 10], False, 110, 30)
+    assert rs._blocks == [(0, 30, 10), (1, 40, 30)] and rs.ray_begin == 30 and rs._local_range(1) == (10, 40)

@@ -18,8 +18,7 @@ for name in ("double_gauss", "image_render"):
     RT = scenes.SCENES[name](ot)
     N = 1_000_003
     RT.trace(N)
-    b, e = dist.shard_range(N)
-    assert RT.rays.N == e - b and RT.rays.ray_begin == b
+    assert RT.rays.N == sum(c for _, _, c in dist.shard_sources(RT.rays.N_list))
     img = RT.detector_image()
     local_alive = torch.tensor([float(RT.rays.N)], dtype=torch.float64, device="cuda")
     dist.allreduce_sum_(local_alive)

@@ -1,6 +1,7 @@
 // otb_detect.cu — detector path: hit finding on stored ray sections (Raytracer._hit_detector,
 // raytracer.py:881-1051) and XYZW histogram binning (RenderImage.render, render_image.py:390-417,
 // misc.binning_indices_2d, misc.py:59-91, CIE observers, observers.py:14-41).
+#include <mutex>
 #include "otb_common.cuh"
 #include "otb_surfaces.cuh"
 #include "otb_media.cuh"
@@ -272,16 +273,24 @@ __global__ void __launch_bounds__(32*OTB_RH_WARPS) render_kernel(BinGrid g, cons
     }
 }
 
-static double* g_obs_d = nullptr;
+// per-device state (one slot per CUDA device: a process may drive several devices from several threads)
+#define OTB_MAX_DEVICES 64
+static double* g_obs_d[OTB_MAX_DEVICES] = {nullptr};
+static bool g_render_smem_set[OTB_MAX_DEVICES] = {false};
+static std::mutex g_dev_mutex;
 int otb_sm_count();
 
 int otb_observer_table(const double** out)
 {
-    if (!g_obs_d) {
-        OTB_CUDA(cudaMalloc(&g_obs_d, sizeof(OTB_OBSERVERS)));
-        OTB_CUDA(cudaMemcpy(g_obs_d, OTB_OBSERVERS, sizeof(OTB_OBSERVERS), cudaMemcpyHostToDevice));
+    int dev = 0;
+    OTB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= OTB_MAX_DEVICES) { otb_set_error("device index out of range"); return OTB_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    if (!g_obs_d[dev]) {
+        OTB_CUDA(cudaMalloc(&g_obs_d[dev], sizeof(OTB_OBSERVERS)));
+        OTB_CUDA(cudaMemcpy(g_obs_d[dev], OTB_OBSERVERS, sizeof(OTB_OBSERVERS), cudaMemcpyHostToDevice));
     }
-    *out = g_obs_d;
+    *out = g_obs_d[dev];
     return OTB_OK;
 }
 
@@ -337,10 +346,12 @@ int otb_render_xyzw(const double* x_d, const double* y_d, const float* w_d, cons
     const double* obs;
     if (int rc = otb_observer_table(&obs)) return rc;
     BinGrid g = otb_make_grid(extent, Nx, Ny);
-    static bool smem_set = false;
-    if (!smem_set) {
+    int dev = 0;
+    OTB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= OTB_MAX_DEVICES) { otb_set_error("device index out of range"); return OTB_ERR_INVALID_ARG; }
+    if (!g_render_smem_set[dev]) {
         OTB_CUDA(cudaFuncSetAttribute(render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OTB_RENDER_SMEM));
-        smem_set = true;
+        g_render_smem_set[dev] = true;
     }
     const int blocks = otb_one_wave_grid(render_kernel, 256, OTB_RENDER_SMEM, otb_sm_count(), (M + 255)/256);
     render_kernel<<<blocks, 256, OTB_RENDER_SMEM, (cudaStream_t)stream>>>(g, obs, M, x_d, y_d, w_d, wl_d, img_d, cnt_d);

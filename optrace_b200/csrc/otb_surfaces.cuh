@@ -43,42 +43,60 @@ __device__ __forceinline__ int bspl_interval(const double* __restrict__ t, int n
     return lo;
 }
 
-// de Boor–Cox recursion (FITPACK fpbspl): the deg+1 non-zero basis functions of degree `deg` at x
-template <int DEG>
-__device__ __forceinline__ void bspl_basis(const double* __restrict__ t, int l, double x, double* h)
+// de Boor–Cox recursion (FITPACK fpbspl): the deg+1 non-zero basis functions of degree `deg` (3 or 4) at x, in
+// h[0..deg] (h[4] = 0 for deg 3).  Compact on purpose: the level loop is rolled and the five lanes of a level are
+// predicated, so the whole recursion is ~150 instructions of code instead of a fully unrolled copy per degree and
+// call site — the numeric-surface kernels are bound by instruction fetch (profiles/r2_zoo_numeric_full_ncu.csv), and
+// every inlined copy of the surface-kind switch carries this code.  Same operations in the same order as before.
+__device__ __forceinline__ void bspl_basis(const double* __restrict__ t, int l, double x, int deg, double* h)
 {
-    double hh[DEG + 1];
-    h[0] = 1.0;
-#pragma unroll
-    for (int j = 1; j <= DEG; ++j) {
-#pragma unroll
-        for (int i = 0; i < j; ++i) hh[i] = h[i];
-        h[0] = 0.0;
-#pragma unroll
-        for (int i = 0; i < j; ++i) {
-            int li = l + i + 1, lj = li - j;
-            double f = hh[i]/(t[li] - t[lj]);
-            h[i] = h[i] + f*(t[li] - x);
-            h[i + 1] = f*(x - t[lj]);
+    double h0 = 1.0, h1 = 0.0, h2 = 0.0, h3 = 0.0, h4 = 0.0;
+#pragma unroll 1
+    for (int j = 1; j <= deg; ++j) {
+        const double g0 = h0, g1 = h1, g2 = h2, g3 = h3;
+        double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0, n4 = 0.0;
+        // i = 0 .. j-1:  f = hh[i]/(t[l+i+1] - t[l+i+1-j]);  h[i] += f*(t[l+i+1] - x);  h[i+1] = f*(x - t[l+i+1-j])
+        {
+            const double ta = t[l + 1], tb = t[l + 1 - j];
+            const double f = g0/(ta - tb);
+            n0 = n0 + f*(ta - x);
+            n1 = f*(x - tb);
         }
+        if (j > 1) {
+            const double ta = t[l + 2], tb = t[l + 2 - j];
+            const double f = g1/(ta - tb);
+            n1 = n1 + f*(ta - x);
+            n2 = f*(x - tb);
+        }
+        if (j > 2) {
+            const double ta = t[l + 3], tb = t[l + 3 - j];
+            const double f = g2/(ta - tb);
+            n2 = n2 + f*(ta - x);
+            n3 = f*(x - tb);
+        }
+        if (j > 3) {
+            const double ta = t[l + 4], tb = t[l + 4 - j];
+            const double f = g3/(ta - tb);
+            n3 = n3 + f*(ta - x);
+            n4 = f*(x - tb);
+        }
+        h0 = n0; h1 = n1; h2 = n2; h3 = n3; h4 = n4;
     }
+    h[0] = h0; h[1] = h1; h[2] = h2; h[3] = h3; h[4] = h4;
 }
 
 // 1-D spline value (nu = 0) or first derivative (nu = 1); extrapolates like splev(ext=0)
 __device__ inline double spline1d(const double* __restrict__ t, int n, const double* __restrict__ c, double x, int nu)
 {
     int l = bspl_interval(t, n, 4, x);
+    double h[5];
+    bspl_basis(t, l, x, nu ? 3 : 4, h);
+    double v = 0.0;
     if (nu == 0) {
-        double h[5];
-        bspl_basis<4>(t, l, x, h);
-        double v = 0.0;
 #pragma unroll
         for (int i = 0; i < 5; ++i) v += c[l - 4 + i]*h[i];
         return v;
     }
-    double h[4];
-    bspl_basis<3>(t, l, x, h);
-    double v = 0.0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int j = l - 3 + i;
@@ -97,22 +115,27 @@ __device__ inline double spline2d(const double* __restrict__ tx, int nx, const d
     int lx = bspl_interval(tx, nx, 4, x), ly = bspl_interval(ty, ny, 4, y);
     int ncy = ny - 5;
     double hx[5], hy[5];
-    if (!dx) bspl_basis<4>(tx, lx, x, hx); else bspl_basis<3>(tx, lx, x, hx);
-    if (!dy) bspl_basis<4>(ty, ly, y, hy); else bspl_basis<3>(ty, ly, y, hy);
+    bspl_basis(tx, lx, x, dx ? 3 : 4, hx);
+    bspl_basis(ty, ly, y, dy ? 3 : 4, hy);
     double v = 0.0;
     int nbx = dx ? 4 : 5, nby = dy ? 4 : 5;
+#pragma unroll 1
     for (int i = 0; i < nbx; ++i) {
         int jx = dx ? (lx - 3 + i) : (lx - 4 + i);
         double row = 0.0;
-        for (int j = 0; j < nby; ++j) {
-            int jy = dy ? (ly - 3 + j) : (ly - 4 + j);
-            double cc;
-            if (dx) cc = 4.0*(c[jx*ncy + jy] - c[(jx - 1)*ncy + jy])/(tx[jx + 4] - tx[jx]);
-            else if (dy) cc = 4.0*(c[jx*ncy + jy] - c[jx*ncy + jy - 1])/(ty[jy + 4] - ty[jy]);
-            else cc = c[jx*ncy + jy];
-            row += cc*hy[j];
+        const double hxi = (i == 0) ? hx[0] : (i == 1) ? hx[1] : (i == 2) ? hx[2] : (i == 3) ? hx[3] : hx[4];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            if (j < nby) {
+                int jy = dy ? (ly - 3 + j) : (ly - 4 + j);
+                double cc;
+                if (dx) cc = 4.0*(c[jx*ncy + jy] - c[(jx - 1)*ncy + jy])/(tx[jx + 4] - tx[jx]);
+                else if (dy) cc = 4.0*(c[jx*ncy + jy] - c[jx*ncy + jy - 1])/(ty[jy + 4] - ty[jy]);
+                else cc = c[jx*ncy + jy];
+                row += cc*hy[j];
+            }
         }
-        v += row*hx[i];
+        v += row*hxi;
     }
     return v;
 }

@@ -86,7 +86,10 @@ __device__ __forceinline__ void bspl_basis(const double* __restrict__ t, int l, 
 }
 
 // 1-D spline value (nu = 0) or first derivative (nu = 1); extrapolates like splev(ext=0)
-__device__ inline double spline1d(const double* __restrict__ t, int n, const double* __restrict__ c, double x, int nu)
+// Out of line (like spline2d and surf_values_full below): the numeric-surface kernels are bound by instruction fetch,
+// so every table / user-function evaluation exists once per kernel image and is CALLED from the hit finder, the edge
+// continuation and the central-difference normals instead of being inlined ~20 times.
+static __device__ __noinline__ double spline1d(const double* __restrict__ t, int n, const double* __restrict__ c, double x, int nu)
 {
     int l = bspl_interval(t, n, 4, x);
     double h[5];
@@ -107,7 +110,7 @@ __device__ inline double spline1d(const double* __restrict__ t, int n, const dou
 }
 
 // tensor-product spline value or partial derivative; arguments clamped to the knot domain like fpbisp
-__device__ inline double spline2d(const double* __restrict__ tx, int nx, const double* __restrict__ ty, int ny,
+static __device__ __noinline__ double spline2d(const double* __restrict__ tx, int nx, const double* __restrict__ ty, int ny,
                                   const double* __restrict__ c, double x, double y, int dx, int dy)
 {
     x = fmin(fmax(x, tx[4]), tx[nx - 5]);
@@ -202,13 +205,17 @@ __device__ inline bool surf_mask(const KSurface& S, double x, double y)
 // (conic_surface.py:57-68, tilted_surface.py:61-74, aspheric_surface.py:51-66,
 //  function_surface_2d.py:133-156, data_surface_2d.py:130-153)
 // ------------------------------------------------------------------------------------------------
-__device__ inline double surf_values_rel(const KSurface& S, const double* __restrict__ aux, double x, double y)
+__device__ __forceinline__ double conic_values_rel(const KSurface& S, double x, double y)
+{
+    double r2 = x*x + y*y;
+    return S.par[OTB_P_RHO]*r2/(1 + sqrt(1 - S.par[OTB_P_KP1RHO2]*r2));
+}
+
+__device__ __forceinline__ double surf_values_rel_body(const KSurface& S, const double* __restrict__ aux, double x, double y)
 {
     switch (S.kind) {
-    case OTB_SURF_CONIC: {
-        double r2 = x*x + y*y;
-        return S.par[OTB_P_RHO]*r2/(1 + sqrt(1 - S.par[OTB_P_KP1RHO2]*r2));
-    }
+    case OTB_SURF_CONIC:
+        return conic_values_rel(S, x, y);
     case OTB_SURF_TILTED:
         return x*S.par[OTB_P_MX] + y*S.par[OTB_P_MY];
     case OTB_SURF_ASPHERE: {
@@ -246,17 +253,48 @@ __device__ inline double surf_values_rel(const KSurface& S, const double* __rest
     }
 }
 
+// the one out-of-line copy of the height switch (all kinds, user functions, splines)
+static __device__ __noinline__ double surf_values_rel(const KSurface* S, const double* aux, double x, double y)
+{
+    return surf_values_rel_body(*S, aux, x, y);
+}
+__device__ __forceinline__ double surf_values_rel(const KSurface& S, const double* __restrict__ aux, double x, double y)
+{
+    return surf_values_rel(&S, aux, x, y);
+}
+
 // Surface.values (surface.py:137-164): absolute height with the radially continued edge
 template <int CAPS>
-__device__ inline double surf_values(const KSurface& S, const double* __restrict__ aux, double x, double y)
+__device__ __forceinline__ double surf_values_body(const KSurface& S, const double* __restrict__ aux, double x, double y)
 {
     if (S.flags & OTB_SF_FLAT) return S.z_max;
     if (CAPS == OTB_CAPS_LENS && S.kind != OTB_SURF_CONIC) return S.z_max;
-    if (surf_mask(S, x, y)) return S.pos[2] + surf_values_rel(S, aux, x - S.pos[0], y - S.pos[1]);
-    if (S.flags & OTB_SF_ROTSYM) return S.pos[2] + S.par[OTB_P_EDGEZ];
-    double r = S.r - OTB_N_EPS;
-    double phi = atan2(y - S.pos[1], x - S.pos[0]);
-    return S.pos[2] + surf_values_rel(S, aux, r*cos(phi), r*sin(phi));
+    if (CAPS == OTB_CAPS_LENS) {
+        if (surf_mask(S, x, y)) return S.pos[2] + conic_values_rel(S, x - S.pos[0], y - S.pos[1]);
+        if (S.flags & OTB_SF_ROTSYM) return S.pos[2] + S.par[OTB_P_EDGEZ];
+        double r = S.r - OTB_N_EPS;
+        double phi = atan2(y - S.pos[1], x - S.pos[0]);
+        return S.pos[2] + conic_values_rel(S, r*cos(phi), r*sin(phi));
+    }
+    double xe = x - S.pos[0], ye = y - S.pos[1];
+    if (!surf_mask(S, x, y)) {
+        if (S.flags & OTB_SF_ROTSYM) return S.pos[2] + S.par[OTB_P_EDGEZ];
+        double r = S.r - OTB_N_EPS;
+        double phi = atan2(ye, xe);
+        xe = r*cos(phi);
+        ye = r*sin(phi);
+    }
+    return S.pos[2] + surf_values_rel_body(S, aux, xe, ye);      // ONE inlined copy of the height switch in here
+}
+static __device__ __noinline__ double surf_values_full(const KSurface* S, const double* aux, double x, double y)
+{
+    return surf_values_body<OTB_CAPS_FULL>(*S, aux, x, y);
+}
+template <int CAPS>
+__device__ __forceinline__ double surf_values(const KSurface& S, const double* __restrict__ aux, double x, double y)
+{
+    if (CAPS == OTB_CAPS_FULL) return surf_values_full(&S, aux, x, y);
+    return surf_values_body<CAPS>(S, aux, x, y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -341,12 +379,10 @@ __device__ inline V3 surf_normal(const KSurface& S, const double* __restrict__ a
 // ------------------------------------------------------------------------------------------------
 // intersection
 // ------------------------------------------------------------------------------------------------
-// Surface._find_hit_handle_abnormal (surface.py:436-479)
-template <int CAPS>
-__device__ inline void handle_abnormal(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, HitResult& h)
+// Surface._find_hit_handle_abnormal (surface.py:436-479).  dz = h.p.z - values(h.p.x, h.p.y), supplied by the caller.
+__device__ __forceinline__ void handle_abnormal_dz(const KSurface& S, const V3& p, const V3& s, HitResult& h, double dz)
 {
-    double zs = surf_values<CAPS>(S, aux, h.p.x, h.p.y);
-    bool dev = fabs(h.p.z - zs) > OTB_C_EPS;
+    bool dev = fabs(dz) > OTB_C_EPS;
     bool beh = p.z > S.z_max + OTB_N_EPS;
     bool neg = h.p.z < p.z - OTB_C_EPS;
     bool bet = (neg || dev) && !beh;
@@ -361,8 +397,19 @@ __device__ inline void handle_abnormal(const KSurface& S, const double* __restri
     }
 }
 
+template <int CAPS>
+__device__ __forceinline__ void handle_abnormal(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, HitResult& h)
+{
+    double zs = surf_values<CAPS>(S, aux, h.p.x, h.p.y);
+    handle_abnormal_dz(S, p, s, h, h.p.z - zs);
+}
+
 // Surface.find_hit (surface.py:307-414): plane for flat surfaces, Illinois regula falsi otherwise.
 // `status` receives OTB_STATUS_TIMEOUT when the 200-iteration limit is reached (surface.py:403).
+// The surface height is evaluated at ONE code site: the two bracket ends (surface.py:340-347), every secant point
+// (:365-367) and the final deviation check of _find_hit_handle_abnormal (:452, whose argument is the last point
+// evaluated, so its height difference is the value already at hand) — same operations on the same operands as the
+// reference, a third of the code.
 template <int CAPS>
 __device__ inline HitResult find_hit_numeric(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
 {
@@ -383,20 +430,33 @@ __device__ inline HitResult find_hit_numeric(const KSurface& S, const double* __
     double t1 = (S.z_min - OTB_C_EPS/10 - p.z)/s.z;
     double t2 = (S.z_max + OTB_C_EPS/10 - p.z)/s.z;
     if (t1 < 0) t1 = -OTB_C_EPS;
-    V3 p1 = along(p, s, t1), p2 = along(p, s, t2);
-    double f1 = p1.z - surf_values<CAPS>(S, aux, p1.x, p1.y);
-    double f2 = p2.z - surf_values<CAPS>(S, aux, p2.x, p2.y);
     bool w = true;
     if (!finite_d(t1) || !finite_d(t2)) w = false;
     if ((t2 - t1) < OTB_C_EPS) w = false;
-    h.p = w ? v3(0.0, 0.0, 0.0) : p1;
-    h.ill = f1*f2 > 0;
+    double f1 = 0.0, f2 = 0.0, dz = 0.0;
+    int phase = 0;                    // 0: bracket start, 1: bracket end, 2: secant points
     int it = 1;
-    while (w) {
-        double ts = t1 - f1/(f2 - f1)*(t2 - t1);
-        V3 pl = along(p, s, ts);
-        double fts = pl.z - surf_values<CAPS>(S, aux, pl.x, pl.y);
-        double prod = fts*f2;
+    h.p = v3(0.0, 0.0, 0.0);
+#pragma unroll 1
+    for (;;) {
+        const double ts = (phase == 0) ? t1 : (phase == 1) ? t2 : t1 - f1/(f2 - f1)*(t2 - t1);
+        const V3 pl = along(p, s, ts);
+        const double fts = pl.z - surf_values<CAPS>(S, aux, pl.x, pl.y);
+        if (phase == 0) {
+            f1 = fts;
+            h.p = pl;                 // kept when the bracket is degenerate (surface.py:352)
+            dz = fts;
+            phase = 1;
+            continue;
+        }
+        if (phase == 1) {
+            f2 = fts;
+            h.ill = f1*f2 > 0;
+            phase = 2;
+            if (!w) break;
+            continue;
+        }
+        const double prod = fts*f2;
         if (prod < 0) {            // case 1: [t2, ts]
             t1 = t2; t2 = ts; f1 = f2; f2 = fts;
         } else if (prod > 0) {     // case 2: [t1, ts], Illinois factor 0.5 on the retained end
@@ -406,16 +466,19 @@ __device__ inline HitResult find_hit_numeric(const KSurface& S, const double* __
         }
         if (fabs(t2 - t1) < OTB_C_EPS/10) {
             h.p = pl;
-            w = false;
-        } else if (it == 200) {
+            dz = fts;
+            break;
+        }
+        if (it == 200) {
             atomicOr(status, OTB_STATUS_TIMEOUT);
             h.p = pl;
-            w = false;
+            dz = fts;
+            break;
         }
         ++it;
     }
     h.hit = surf_mask(S, h.p.x, h.p.y);
-    handle_abnormal<CAPS>(S, aux, p, s, h);
+    handle_abnormal_dz(S, p, s, h, dz);
     return h;
 }
 
@@ -459,34 +522,28 @@ __device__ inline HitResult find_hit_conic(const KSurface& S, const V3& p, const
     return h;
 }
 
-// TiltedSurface.find_hit (tilted_surface.py:91-123)
-template <int CAPS>
-__device__ inline HitResult find_hit_tilted(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
-{
-    HitResult h;
-    const V3 n = v3(S.par[OTB_P_NX], S.par[OTB_P_NY], S.par[OTB_P_NZ]);
-    double t_denom = dot3(s, n);
-    bool nz = t_denom != 0;
-    V3 d = v3(S.pos[0] - p.x, S.pos[1] - p.y, S.pos[2] - p.z);
-    double t = dot3(d, n)/(nz ? t_denom : 1e-12);
-    h.p = along(p, s, t);
-    h.hit = surf_mask(S, h.p.x, h.p.y) && nz;
-    h.ill = false;
-    if (!h.hit) h = find_hit_numeric<CAPS>(S, aux, p, s, status);
-    handle_abnormal<CAPS>(S, aux, p, s, h);
-    return h;
-}
-
+// TiltedSurface.find_hit (tilted_surface.py:91-123): analytic plane hit; rays that miss the disc go through the
+// numeric finder (radially continued edge).  Shares the ONE inlined copy of find_hit_numeric with the other kinds.
 template <int CAPS>
 __device__ inline HitResult surf_find_hit(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
 {
-    switch (S.kind) {
-    case OTB_SURF_CONIC: return find_hit_conic(S, p, s);
-    case OTB_SURF_TILTED:
-        if (CAPS == OTB_CAPS_FULL) return find_hit_tilted<CAPS>(S, aux, p, s, status);
-        return find_hit_numeric<CAPS>(S, aux, p, s, status);
-    default: return find_hit_numeric<CAPS>(S, aux, p, s, status);
+    if (S.kind == OTB_SURF_CONIC) return find_hit_conic(S, p, s);
+    const bool tilted = (CAPS == OTB_CAPS_FULL) && S.kind == OTB_SURF_TILTED;
+    HitResult h;
+    h.hit = false;
+    if (tilted) {
+        const V3 n = v3(S.par[OTB_P_NX], S.par[OTB_P_NY], S.par[OTB_P_NZ]);
+        double t_denom = dot3(s, n);
+        bool nz = t_denom != 0;
+        V3 d = v3(S.pos[0] - p.x, S.pos[1] - p.y, S.pos[2] - p.z);
+        double t = dot3(d, n)/(nz ? t_denom : 1e-12);
+        h.p = along(p, s, t);
+        h.hit = surf_mask(S, h.p.x, h.p.y) && nz;
+        h.ill = false;
     }
+    if (!h.hit) h = find_hit_numeric<CAPS>(S, aux, p, s, status);
+    if (tilted) handle_abnormal<CAPS>(S, aux, p, s, h);
+    return h;
 }
 
 // SphericalSurface.sphere_projection (spherical_surface.py:36-97), in place on (x, y) given z

@@ -119,7 +119,10 @@ __device__ __forceinline__ void store_step(const KScene& sc, const TraceArgs& a,
     }
 }
 
-template <bool POL, int CAPS>
+// GEN: the rays are drawn inside the kernel (fused RaySource.create_rays).  A template parameter, not a run-time
+// branch: the generator is ~5000 instructions, and the kernels of injected / pre-generated bundles (the default) are
+// sensitive to their code footprint (cosine_surfaces: 8.9 ms without, 16 ms with the generator compiled in).
+template <bool POL, int CAPS, bool GEN>
 __global__ void __launch_bounds__(OTB_THREADS_OF(CAPS), OTB_BLOCKS_OF(CAPS))
 trace_store_kernel(const __grid_constant__ TraceArgs a)
 {
@@ -143,13 +146,12 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
 
     const int64_t Nnt = N*(int64_t)nt;
 
-    const bool generate = a.G.nsrc > 0;
     for (int64_t base = a.k_begin + (int64_t)blockIdx.x*blockDim.x; base < a.k_end; base += (int64_t)gridDim.x*blockDim.x) {
         const int64_t ray = base + threadIdx.x;
         const bool valid = ray < a.k_end;
         const int64_t rr = valid ? ray : a.k_begin;  // clamp so that every lane addresses valid memory
         RayState r;
-        if (generate) {
+        if (GEN) {
             // fused RaySource.create_rays: the ray is drawn here (Philox counter = global ray id) instead of being
             // written by a generator kernel and read back
             GenRay gr;
@@ -270,15 +272,17 @@ static int launch_trace_store_range(const OtbScene* scene, TraceArgs& a, cudaStr
     const int64_t aux_bytes = ((scene->n_aux*(int64_t)sizeof(double) + 15)/16)*16;
     if (scene->caps == OTB_CAPS_FULL && scene->n_aux > 0 && aux_bytes <= OTB_AUX_SMEM_MAX) a.aux_smem_bytes = (int)aux_bytes;
     size_t smem = (size_t)a.aux_smem_bytes + 16 + sizeof(int)*OTB_NMSG*a.out.nt;
-#define OTB_LAUNCH_STORE(POL, CAPS) do { \
+#define OTB_LAUNCH_STORE_G(POL, CAPS, GEN) do { \
         const int threads = OTB_THREADS_OF(CAPS); \
         const int64_t blocks_needed = (a.k_end - a.k_begin + threads - 1)/threads; \
         if (smem > 48*1024) { \
-            cudaError_t ea = cudaFuncSetAttribute(trace_store_kernel<POL, CAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            cudaError_t ea = cudaFuncSetAttribute(trace_store_kernel<POL, CAPS, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (ea != cudaSuccess) return otb_cuda_fail(ea, "cudaFuncSetAttribute(trace_store_kernel)"); \
         } \
-        int blocks = otb_one_wave_grid(trace_store_kernel<POL, CAPS>, threads, smem, sm_count, blocks_needed); \
-        trace_store_kernel<POL, CAPS><<<blocks, threads, smem, stream>>>(a); } while (0)
+        int blocks = otb_one_wave_grid(trace_store_kernel<POL, CAPS, GEN>, threads, smem, sm_count, blocks_needed); \
+        trace_store_kernel<POL, CAPS, GEN><<<blocks, threads, smem, stream>>>(a); } while (0)
+#define OTB_LAUNCH_STORE(POL, CAPS) do { if (a.G.nsrc > 0) OTB_LAUNCH_STORE_G(POL, CAPS, true); \
+        else OTB_LAUNCH_STORE_G(POL, CAPS, false); } while (0)
 #if OTB_SPEC
     if (!otb_scene_equal(scene->k, K_SPEC_HOST)) {
         otb_set_error("this engine build is specialised for a different scene");

@@ -140,7 +140,8 @@ __device__ __forceinline__ void render_step(const KScene& sc, const RenderArgs& 
     }
 }
 
-template <bool POL, int CAPS>
+// GEN: rays are drawn in the kernel (a template parameter: no generator code in the kernels of pre-generated bundles)
+template <bool POL, int CAPS, bool GEN>
 __global__ void __launch_bounds__(OTB_RENDER_THREADS, OTB_MINBLOCKS(CAPS))
 trace_render_kernel(const __grid_constant__ RenderArgs a)
 {
@@ -159,12 +160,11 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
     if (threadIdx.x < 4*OTB_MAX_DET) srng[threadIdx.x] = (threadIdx.x & 1) ? 0ull : ~0ull;
     __syncthreads();
 
-    const bool generate = a.G.nsrc > 0;
     for (int64_t base = a.k_begin + (int64_t)blockIdx.x*blockDim.x; base < a.k_end; base += (int64_t)gridDim.x*blockDim.x) {
         const int64_t ray = base + threadIdx.x;
         const bool valid = ray < a.k_end;
         RayState r;
-        if (generate) {
+        if (GEN) {
             GenRay gr;
             generate_ray(a.G, valid ? ray : a.k_begin, gr);
             if (valid && gr.neg_dir) atomicOr(a.status, OTB_STATUS_NEG_DIR);
@@ -231,9 +231,11 @@ trace_render_kernel(const __grid_constant__ RenderArgs a)
         if (smsgs[i]) atomicAdd(&a.msgs[i], (unsigned long long)smsgs[i]);
 }
 
-#define OTB_LAUNCH_RENDER(POL, CAPS) do { \
-        int blocks = otb_one_wave_grid(trace_render_kernel<POL, CAPS>, OTB_RENDER_THREADS, smem, otb_sm_count(), blocks_needed); \
-        trace_render_kernel<POL, CAPS><<<blocks, OTB_RENDER_THREADS, smem, st>>>(a); } while (0)
+#define OTB_LAUNCH_RENDER_G(POL, CAPS, GEN) do { \
+        int blocks = otb_one_wave_grid(trace_render_kernel<POL, CAPS, GEN>, OTB_RENDER_THREADS, smem, otb_sm_count(), blocks_needed); \
+        trace_render_kernel<POL, CAPS, GEN><<<blocks, OTB_RENDER_THREADS, smem, st>>>(a); } while (0)
+#define OTB_LAUNCH_RENDER(POL, CAPS) do { if (a.G.nsrc > 0) OTB_LAUNCH_RENDER_G(POL, CAPS, true); \
+        else OTB_LAUNCH_RENDER_G(POL, CAPS, false); } while (0)
 
 int otb_observer_table(const double** out);
 int otb_check_sources(const OtbSource* sources_h, int n_sources, int64_t N);

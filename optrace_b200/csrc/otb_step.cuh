@@ -96,7 +96,9 @@ __device__ __forceinline__ void hurb_props(const KSurface& S, double x, double y
 
 // One sequential step.  On entry `r` holds section i, on exit section i+1 (p, w, pol, n) and the new direction.
 // za, zb: standard normal deviates for HURB (only read when the step bends rays).
-template <bool POL, int CAPS>
+// HOT = 1: lens front / back at a non-flat asphere / function / data surface only (the inlined numeric-surface step of
+// trace_step); everything else of the step is compiled out.
+template <bool POL, int CAPS, int HOT = 0>
 __device__ __forceinline__ void trace_step_full(const KScene& sc, const double* __restrict__ aux, const OtbStep& st, RayState& r,
                                                 StepFlags& fl, double za, double zb, int* status)
 {
@@ -111,14 +113,14 @@ __device__ __forceinline__ void trace_step_full(const KScene& sc, const double* 
     bool hit = false;
 
     if (hw) {
-        HitResult h = surf_find_hit<CAPS>(S, aux, r.p, r.s, status);
+        HitResult h = surf_find_hit<CAPS, HOT>(S, aux, r.p, r.s, status);
         p_n = h.p;
         hit = h.hit;
         fl.ill = h.ill;
     }
     const bool hwh = hw && hit, hwnh = hw && !hit;
 
-    if (st.role <= OTB_STEP_IDEAL_LENS) {
+    if (HOT || st.role <= OTB_STEP_IDEAL_LENS) {
         // ---- Lens front / back / ideal lens (raytracer.py:314-370) ----
         if (hwnh) {
             w_n = 0.0f;
@@ -128,7 +130,7 @@ __device__ __forceinline__ void trace_step_full(const KScene& sc, const double* 
         const double n2 = medium_n(sc.media[st.medium_after], aux, r.wl);
         if (n2 < 1.0) atomicOr(status, OTB_STATUS_NBELOW1);
         if (hwh) {
-            if (st.role == OTB_STEP_IDEAL_LENS) {
+            if (!HOT && st.role == OTB_STEP_IDEAL_LENS) {
                 // Raytracer.__refraction_ideal_lens (raytracer.py:720-759)
                 const V3 s0 = r.s;
                 const double f = 1000/st.D;
@@ -141,7 +143,7 @@ __device__ __forceinline__ void trace_step_full(const KScene& sc, const double* 
                 compute_polarization<POL>(s0, r.s, r.pol, pol_n, a, b);
             } else {
                 // Raytracer.__refraction (raytracer.py:761-829)
-                const V3 nrm = surf_normal<CAPS>(S, aux, p_n.x, p_n.y);
+                const V3 nrm = surf_normal<CAPS, HOT>(S, aux, p_n.x, p_n.y);
                 const double n1 = r.n;
                 const double ns = dot3(nrm, r.s);
                 const double N = n1/n2;
@@ -277,6 +279,12 @@ __device__ __forceinline__ void trace_step(const KScene& sc, const double* __res
     } else if (st.role == OTB_STEP_APERTURE && !st.hurb && (S.flags & OTB_SF_FLAT) && !(S.flags & OTB_SF_ROTATED)
                && (S.kind == OTB_SURF_CIRCLE || S.kind == OTB_SURF_RECT || S.kind == OTB_SURF_RING)) {
         done = fast_flat_aperture_step(sc, S, r, fl);
+    } else if (CAPS == OTB_CAPS_FULL && st.role <= OTB_STEP_LENS_BACK && !(S.flags & OTB_SF_FLAT)
+               && (S.kind == OTB_SURF_FUNC || S.kind == OTB_SURF_DATA || S.kind == OTB_SURF_ASPHERE)) {
+        // numeric surfaces: for them the full step IS the hot path — inlined here (scene in the constant bank, no
+        // call per height evaluation) with everything but the lens branch compiled out
+        trace_step_full<POL, CAPS, 1>(sc, aux, st, r, fl, za, zb, status);
+        done = true;
     }
 #if OTB_STEP_OOL
     if (!done) {

@@ -302,7 +302,9 @@ __device__ __forceinline__ double surf_values(const KSurface& S, const double* _
 // TiltedSurface.normals (tilted_surface.py:76-89), FunctionSurface2D.normals
 // (function_surface_2d.py:193-253), DataSurface2D.normals (data_surface_2d.py:155-196)
 // ------------------------------------------------------------------------------------------------
-template <int CAPS>
+// HOT = 1: the inlined instantiation of the numeric-surface lens step in the trace loop (asphere / function / data
+// surfaces only, see trace_step): no conic code, heights evaluated inline at ONE code site per loop.
+template <int CAPS, int HOT = 0>
 __device__ inline V3 surf_normal(const KSurface& S, const double* __restrict__ aux, double x, double y)
 {
     const int k = S.kind;
@@ -312,7 +314,7 @@ __device__ inline V3 surf_normal(const KSurface& S, const double* __restrict__ a
     const double x0 = S.pos[0], y0 = S.pos[1];
     const double dx = x - x0, dy = y - y0;
 
-    if (k == OTB_SURF_CONIC) {
+    if (!HOT && k == OTB_SURF_CONIC) {
         double rho = S.par[OTB_P_RHO];
         if (S.par[OTB_P_K] == 0.0) {
             double rho2 = S.par[OTB_P_RHO2];
@@ -330,7 +332,7 @@ __device__ inline V3 surf_normal(const KSurface& S, const double* __restrict__ a
         }
         return v3(n_r*c, n_r*sn, sqrt(1 - n_r*n_r));
     }
-    if (k == OTB_SURF_TILTED) return v3(S.par[OTB_P_NX], S.par[OTB_P_NY], S.par[OTB_P_NZ]);
+    if (!HOT && k == OTB_SURF_TILTED) return v3(S.par[OTB_P_NX], S.par[OTB_P_NY], S.par[OTB_P_NZ]);
 
     const bool analytic = (k == OTB_SURF_ASPHERE) || (k == OTB_SURF_DATA) || (k == OTB_SURF_FUNC && (S.flags & OTB_SF_HAS_DERIV));
     if (analytic) {
@@ -370,8 +372,25 @@ __device__ inline V3 surf_normal(const KSurface& S, const double* __restrict__ a
     // central differences (surface.py:266-283)
     double eps = S.par[OTB_P_FDEPS];
     V3 n;
-    n.x = surf_values_rel(S, aux, dx - eps, dy) - surf_values_rel(S, aux, dx + eps, dy);
-    n.y = surf_values_rel(S, aux, dx, dy - eps) - surf_values_rel(S, aux, dx, dy + eps);
+    if (HOT) {
+        // the four heights through one inlined copy of the height switch (rolled loop)
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3_ = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            const double xx = (q == 0) ? dx - eps : (q == 1) ? dx + eps : dx;
+            const double yy = (q == 2) ? dy - eps : (q == 3) ? dy + eps : dy;
+            const double v = surf_values_rel_body(S, aux, xx, yy);
+            v0 = (q == 0) ? v : v0;
+            v1 = (q == 1) ? v : v1;
+            v2 = (q == 2) ? v : v2;
+            v3_ = (q == 3) ? v : v3_;
+        }
+        n.x = v0 - v1;
+        n.y = v2 - v3_;
+    } else {
+        n.x = surf_values_rel(S, aux, dx - eps, dy) - surf_values_rel(S, aux, dx + eps, dy);
+        n.y = surf_values_rel(S, aux, dx, dy - eps) - surf_values_rel(S, aux, dx, dy + eps);
+    }
     n.z = 2*eps;
     return unit3(n);
 }
@@ -410,12 +429,12 @@ __device__ __forceinline__ void handle_abnormal(const KSurface& S, const double*
 // (:365-367) and the final deviation check of _find_hit_handle_abnormal (:452, whose argument is the last point
 // evaluated, so its height difference is the value already at hand) — same operations on the same operands as the
 // reference, a third of the code.
-template <int CAPS>
+template <int CAPS, int HOT = 0>
 __device__ inline HitResult find_hit_numeric(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
 {
     HitResult h;
     h.ill = false;
-    if (S.flags & OTB_SF_FLAT) {
+    if (!HOT && (S.flags & OTB_SF_FLAT)) {
         double t = (S.pos[2] - p.z)/s.z;
         h.p = along(p, s, t);
         h.hit = surf_mask(S, h.p.x, h.p.y);
@@ -441,7 +460,7 @@ __device__ inline HitResult find_hit_numeric(const KSurface& S, const double* __
     for (;;) {
         const double ts = (phase == 0) ? t1 : (phase == 1) ? t2 : t1 - f1/(f2 - f1)*(t2 - t1);
         const V3 pl = along(p, s, ts);
-        const double fts = pl.z - surf_values<CAPS>(S, aux, pl.x, pl.y);
+        const double fts = pl.z - (HOT ? surf_values_body<CAPS>(S, aux, pl.x, pl.y) : surf_values<CAPS>(S, aux, pl.x, pl.y));
         if (phase == 0) {
             f1 = fts;
             h.p = pl;                 // kept when the bracket is degenerate (surface.py:352)
@@ -524,9 +543,10 @@ __device__ inline HitResult find_hit_conic(const KSurface& S, const V3& p, const
 
 // TiltedSurface.find_hit (tilted_surface.py:91-123): analytic plane hit; rays that miss the disc go through the
 // numeric finder (radially continued edge).  Shares the ONE inlined copy of find_hit_numeric with the other kinds.
-template <int CAPS>
+template <int CAPS, int HOT = 0>
 __device__ inline HitResult surf_find_hit(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
 {
+    if (HOT) return find_hit_numeric<CAPS, 1>(S, aux, p, s, status);
     if (S.kind == OTB_SURF_CONIC) return find_hit_conic(S, p, s);
     const bool tilted = (CAPS == OTB_CAPS_FULL) && S.kind == OTB_SURF_TILTED;
     HitResult h;

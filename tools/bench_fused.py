@@ -8,7 +8,11 @@ from optrace_b200 import engine
 from optrace_b200.scene import detector_record
 import scenes
 engine.ensure_init(); ot.global_options.show_warnings = False
-RT = scenes.image_render(ot); print("specialised", RT.compile())
+RT = scenes.image_render(ot)
+if "spec" in sys.argv[1:]:
+    print("specialised", RT.compile())
+else:
+    RT.use_specialised_kernels = False
 scene = RT._scene_handle()
 N = 10_000_000
 rays = RT._generate(np.array([N]), 0, N, 3)

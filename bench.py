@@ -207,9 +207,13 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        """Started BEFORE the warm-up: nvidia-smi's own start-up (NVML initialisation, enumeration of every GPU of
+        the box) holds driver locks for up to a second and stalls kernel launches of this process while it lasts —
+        inside the timed region it doubled ms_per_step on some boxes (5.3 -> 12.4 ms).  mark() opens the window whose
+        samples are reported (the timed regions); the polling itself (one NVML query per 100 ms) is harmless."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -217,6 +221,16 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
+
+    def wait_first(self, timeout=5.0):
+        """block until the sampler has delivered its first row (its start-up is over)"""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        """samples from here on count (called right before the first timed region)"""
+        self.rows = self.rows[-1:]
 
     def stop(self):
         if self.proc:
@@ -297,6 +311,9 @@ def run_gpu(args):
     from optrace_b200.ray_storage import split_rays
     N_list = dist.broadcast_ints(split_rays(N_total, [rs.power for rs in RT.ray_sources]), dev)
     snap = None
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     # burn-in before the W warm-up steps of the contract: on a fresh box the first steps still grow the caching
     # allocator (cudaMalloc of the 8 GB ray store, image and hit buffers) and page the library in
     for _ in range(max(0, 8 - args.warmup)):
@@ -304,9 +321,9 @@ def run_gpu(args):
     for _ in range(args.warmup):
         step_resident(False)
     barrier()
-    clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.wait_first()
+        clocks.mark()
     t0, t1 = ev(), ev()
     t0.record()
     for _ in range(args.steps):

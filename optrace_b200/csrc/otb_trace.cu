@@ -10,15 +10,21 @@
 #include "otb_gen.cuh"
 
 #define OTB_TRACE_THREADS 128
-// Scenes with numeric surfaces (CAPS_FULL) run one block of 384 threads per SM instead of three of 128 (same 12 warps
-// at 168 registers): the block then owns the SM's shared memory and stages the scene's aux tables in it — spline
+// Scenes with numeric surfaces (CAPS_FULL) run ONE block of 512 threads per SM (16 warps at 128 registers; measured on
+// cosine_surfaces / zoo_numeric: 256 threads 11.2 / 120 ms, 384: 8.7 / 106, 448: 9.2 / 106, 512: 7.6 / 89, 640: 9.5 / 89,
+// 768: 10.5 / 91 ms per 10 M rays — the kernel is latency-bound, more warps help until the spills take over): the
+// block then owns the SM's shared memory and stages the scene's aux tables in it — spline
 // knots / coefficients of DataSurfaces, asphere polynomials, tabulated media and filters — with ONE bulk asynchronous
 // copy (TMA, cp.async.bulk + mbarrier) when they fit; every table lookup of the Illinois iteration and of the normal
 // (a 5 x 5 coefficient patch plus knots per spline evaluation, ~13 evaluations per hit) then reads shared memory
 // instead of L1/L2 (data_surface_2d.py:104, 130-153).  Larger tables stay in global memory (L2 resident).
-#define OTB_TRACE_THREADS_FULL 384
+#ifndef OTB_TRACE_THREADS_FULL
+#define OTB_TRACE_THREADS_FULL 512      // scenes with asphere / function / data surfaces
+#endif
+#ifndef OTB_TRACE_THREADS_FULL_FLAT
+#define OTB_TRACE_THREADS_FULL_FLAT 384 // CAPS_FULL for other reasons (HURB apertures, tilted planes, tabulated media): 168 registers
+#endif
 #define OTB_AUX_SMEM_MAX (200*1024)
-#define OTB_THREADS_OF(CAPS) ((CAPS) == OTB_CAPS_FULL ? OTB_TRACE_THREADS_FULL : OTB_TRACE_THREADS)
 #define OTB_BLOCKS_OF(CAPS) ((CAPS) == OTB_CAPS_FULL ? 1 : OTB_MINBLOCKS(CAPS))
 
 // one bulk asynchronous copy global -> shared (TMA engine), completion on an mbarrier; bytes: multiple of 16
@@ -122,8 +128,10 @@ __device__ __forceinline__ void store_step(const KScene& sc, const TraceArgs& a,
 // GEN: the rays are drawn inside the kernel (fused RaySource.create_rays).  A template parameter, not a run-time
 // branch: the generator is ~5000 instructions, and the kernels of injected / pre-generated bundles (the default) are
 // sensitive to their code footprint (cosine_surfaces: 8.9 ms without, 16 ms with the generator compiled in).
-template <bool POL, int CAPS, bool GEN>
-__global__ void __launch_bounds__(OTB_THREADS_OF(CAPS), OTB_BLOCKS_OF(CAPS))
+// THREADS: block size the register allocation is made for (see above; measured on hurb_square / hurb_pinhole:
+// 384 threads 2.27 / 1.78 ms, 512 threads 2.43 / 2.04 ms per 10 M rays — the opposite of the numeric-surface scenes).
+template <bool POL, int CAPS, bool GEN, int THREADS>
+__global__ void __launch_bounds__(THREADS, OTB_BLOCKS_OF(CAPS))
 trace_store_kernel(const __grid_constant__ TraceArgs a)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -264,6 +272,31 @@ int otb_launch_trace_store(const OtbScene* scene, const OtbRays* rays, const Otb
     return OTB_OK;
 }
 
+template <bool POL, int CAPS, bool GEN, int THREADS>
+static int launch_store_threads(const TraceArgs& a, cudaStream_t stream, int sm_count, size_t smem)
+{
+    const int64_t blocks_needed = (a.k_end - a.k_begin + THREADS - 1)/THREADS;
+    if (smem > 48*1024) {
+        cudaError_t ea = cudaFuncSetAttribute(trace_store_kernel<POL, CAPS, GEN, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ea != cudaSuccess) return otb_cuda_fail(ea, "cudaFuncSetAttribute(trace_store_kernel)");
+    }
+    const int blocks = otb_one_wave_grid(trace_store_kernel<POL, CAPS, GEN, THREADS>, THREADS, smem, sm_count, blocks_needed);
+    trace_store_kernel<POL, CAPS, GEN, THREADS><<<blocks, THREADS, smem, stream>>>(a);
+    return OTB_OK;
+}
+
+// block size per capability level; fused generation keeps one block size (fewer instantiations of the largest kernels)
+template <bool POL, int CAPS, bool GEN>
+static int launch_store_caps(const TraceArgs& a, cudaStream_t stream, int sm_count, size_t smem, bool numeric)
+{
+    if constexpr (CAPS != OTB_CAPS_FULL) return launch_store_threads<POL, CAPS, GEN, OTB_TRACE_THREADS>(a, stream, sm_count, smem);
+    else if constexpr (GEN) return launch_store_threads<POL, CAPS, GEN, OTB_TRACE_THREADS_FULL>(a, stream, sm_count, smem);
+    else {
+        if (numeric) return launch_store_threads<POL, CAPS, GEN, OTB_TRACE_THREADS_FULL>(a, stream, sm_count, smem);
+        return launch_store_threads<POL, CAPS, GEN, OTB_TRACE_THREADS_FULL_FLAT>(a, stream, sm_count, smem);
+    }
+}
+
 static int launch_trace_store_range(const OtbScene* scene, TraceArgs& a, cudaStream_t stream, int sm_count)
 {
     // aux tables in shared memory (TMA bulk copy at kernel start) for the numeric-surface kernels when they fit
@@ -272,17 +305,15 @@ static int launch_trace_store_range(const OtbScene* scene, TraceArgs& a, cudaStr
     const int64_t aux_bytes = ((scene->n_aux*(int64_t)sizeof(double) + 15)/16)*16;
     if (scene->caps == OTB_CAPS_FULL && scene->n_aux > 0 && aux_bytes <= OTB_AUX_SMEM_MAX) a.aux_smem_bytes = (int)aux_bytes;
     size_t smem = (size_t)a.aux_smem_bytes + 16 + sizeof(int)*OTB_NMSG*a.out.nt;
-#define OTB_LAUNCH_STORE_G(POL, CAPS, GEN) do { \
-        const int threads = OTB_THREADS_OF(CAPS); \
-        const int64_t blocks_needed = (a.k_end - a.k_begin + threads - 1)/threads; \
-        if (smem > 48*1024) { \
-            cudaError_t ea = cudaFuncSetAttribute(trace_store_kernel<POL, CAPS, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (ea != cudaSuccess) return otb_cuda_fail(ea, "cudaFuncSetAttribute(trace_store_kernel)"); \
-        } \
-        int blocks = otb_one_wave_grid(trace_store_kernel<POL, CAPS, GEN>, threads, smem, sm_count, blocks_needed); \
-        trace_store_kernel<POL, CAPS, GEN><<<blocks, threads, smem, stream>>>(a); } while (0)
-#define OTB_LAUNCH_STORE(POL, CAPS) do { if (a.G.nsrc > 0) OTB_LAUNCH_STORE_G(POL, CAPS, true); \
-        else OTB_LAUNCH_STORE_G(POL, CAPS, false); } while (0)
+#define OTB_LAUNCH_STORE(POL, CAPS) do { \
+        const int rc_ = (a.G.nsrc > 0) ? launch_store_caps<POL, CAPS, true>(a, stream, sm_count, smem, numeric) \
+                                       : launch_store_caps<POL, CAPS, false>(a, stream, sm_count, smem, numeric); \
+        if (rc_) return rc_; } while (0)
+    bool numeric = false;
+    for (int i = 0; i < scene->k.n_steps; ++i) {
+        const KSurface& S = scene->k.surf[scene->k.steps[i].surface];
+        if (!(S.flags & OTB_SF_FLAT) && (S.kind == OTB_SURF_FUNC || S.kind == OTB_SURF_DATA || S.kind == OTB_SURF_ASPHERE)) numeric = true;
+    }
 #if OTB_SPEC
     if (!otb_scene_equal(scene->k, K_SPEC_HOST)) {
         otb_set_error("this engine build is specialised for a different scene");

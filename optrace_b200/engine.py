@@ -613,6 +613,27 @@ def assemble_tiles(shape, header: np.ndarray, packed: np.ndarray):
     return out[:Ny, :Nx], (out, ids)
 
 
+_assembler = None
+
+
+def assemble_submit(shape, ready_event, hdr_t, buf_t):
+    """assemble_tiles on the worker thread once `ready_event` (the pinned copy) has completed.  Returns a future of
+    (dense view, pool token), or of None when the tile capacity overflowed (the caller then takes the dense path)."""
+    global _assembler
+    if _assembler is None:
+        import concurrent.futures
+        _assembler = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="otb-assemble")
+
+    def task():
+        ready_event.synchronize()           # releases the GIL while waiting
+        h = hdr_t.numpy()
+        if int(h[1]):
+            return None
+        return assemble_tiles(shape, h, buf_t.numpy())
+
+    return _assembler.submit(task)
+
+
 def release_dense(token) -> None:
     """give a padded host image back to the pool (called when its RenderImage dies): the written tiles are zeroed"""
     out, ids = token

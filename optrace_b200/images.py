@@ -265,6 +265,10 @@ class RenderImage:
                 self._data_dev.record_stream(side)
                 self._host_ready = torch.cuda.Event()
                 self._host_ready.record(side)
+            if cap:
+                # the host-side scatter of the tiles into the dense image runs on a worker thread as soon as the copy
+                # has landed (the caller is usually blocked in the next trace's status readback by then)
+                self._bg = engine.assemble_submit(tuple(self._data_dev.shape), self._host_ready, self._host_hdr, self._host_buf)
         return self
 
     def _materialise(self):
@@ -272,6 +276,8 @@ class RenderImage:
             if self._data_dev is None:
                 raise RuntimeError("Image was not calculated/rendered yet.")
             if self._host_buf is not None:
+                bg = self.__dict__.pop("_bg", None)
+                done = bg.result() if bg is not None else None       # (dense view, pool token) or None (overflow)
                 self._host_ready.synchronize()
                 hdr = getattr(self, "_host_hdr", None)
                 if hdr is None:
@@ -286,7 +292,9 @@ class RenderImage:
                         self._data = self._data_dev.cpu().numpy()
                         self.transferred_bytes = self._data.nbytes + h.nbytes + self._host_buf.numel()*8
                     else:
-                        self._data, self._dense_token = engine.assemble_tiles(self._data_dev.shape, h, self._host_buf.numpy())
+                        if done is None:
+                            done = engine.assemble_tiles(self._data_dev.shape, h, self._host_buf.numpy())
+                        self._data, self._dense_token = done
                         self.transferred_bytes = h.nbytes + self._host_buf.numel()*8
                     engine.pinned_give(self._host_buf)
                     engine.pinned_give(hdr)
@@ -299,6 +307,11 @@ class RenderImage:
 
     def __del__(self):
         try:
+            bg = self.__dict__.pop("_bg", None)
+            if bg is not None:                 # download started but never consumed: take the result back
+                done = bg.result()
+                if done is not None:
+                    self._dense_token = done[1]
             tok = self.__dict__.get("_dense_token")
             if tok is not None:
                 from . import engine

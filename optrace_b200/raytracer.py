@@ -109,9 +109,10 @@ class Raytracer(Group):
         """plain-value state of everything the flattened scene depends on.  The deep walk (~0.1 ms) is reused while
         no attribute of any scene object was assigned (scene epoch, _state.py); positions are re-read every time
         so that in-place edits of a `pos` array are still noticed."""
-        quick = (_state.EPOCH[0], len(self.elements), tuple(self.outline), self.no_pol, self.use_hurb, self.HURB_FACTOR,
+        raw = self._elements          # unsorted: the sort by z (a `pos` evaluation per element) is not needed for a key
+        quick = (_state.EPOCH[0], len(raw), tuple(self.outline), self.no_pol, self.use_hurb, self.HURB_FACTOR,
                  self.arithmetic,
-                 id(self.n0), tuple((id(el), el._front.pos.tobytes()) for el in self.elements),
+                 id(self.n0), tuple((id(el), el._front.pos.tobytes()) for el in raw),
                  tuple((id(rs), id(rs.or_func)) for rs in self.ray_sources if rs.orientation == "Function"))
         cache = self.__dict__.get("_geom_cache")
         if cache is not None and cache[0] == quick:

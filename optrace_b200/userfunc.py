@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ast
 import hashlib
+import os
 import inspect
 import math
 import pathlib
@@ -436,7 +437,9 @@ def build_specialised_library(user_funcs, api_only: bool = False) -> pathlib.Pat
     api_only: only the array entry points (Surface.find_hit / normals / values on a stand-alone surface) see the
     callables; the trace kernels are linked from the base build (much faster to compile)."""
     header = generate_header(user_funcs)
-    key = hashlib.sha256((header + build.source_digest() + ("api" if api_only else "")).encode()).hexdigest()[:16]
+    # OTB_NVCC_EXTRA: extra nvcc flags for variant builds (kernel-tuning experiments, e.g. -DOTB_TRACE_THREADS_FULL=512)
+    extra = os.environ.get("OTB_NVCC_EXTRA", "").split()
+    key = hashlib.sha256((header + build.source_digest() + ("api" if api_only else "") + " ".join(extra)).encode()).hexdigest()[:16]
     JIT_DIR.mkdir(parents=True, exist_ok=True)
     lib = JIT_DIR / f"libotb_{key}.so"
     if lib.exists():
@@ -444,7 +447,7 @@ def build_specialised_library(user_funcs, api_only: bool = False) -> pathlib.Pat
     hdr = JIT_DIR / f"user_{key}.cuh"
     hdr.write_text(header)
     objdir = JIT_DIR / f"obj_{key}"
-    flags = [f'-DOTB_USER_FUNCS_H="{hdr}"']
+    flags = [f'-DOTB_USER_FUNCS_H="{hdr}"', *extra]
     build.build_library()
     keep = ("otb_api.cu",) if api_only else ("otb_api.cu", "otb_trace.cu", "otb_render.cu")
     if any(k == "orient" for k, _, _ in user_funcs):

@@ -48,6 +48,7 @@ def parse():
                     help="trace kernel build: generic (scene in the constant bank, rolled step loop) or the "
                          "scene-specialised variant of Raytracer.compile()")
     ap.add_argument("--no-compare", action="store_true", help="skip timing the other engine build")
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not run the nvidia-smi clock sampler")
     return ap.parse_args()
 
 
@@ -312,7 +313,7 @@ def run_gpu(args):
     N_list = dist.broadcast_ints(split_rays(N_total, [rs.power for rs in RT.ray_sources]), dev)
     snap = None
     clocks = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         clocks.start()
     # burn-in before the W warm-up steps of the contract: on a fresh box the first steps still grow the caching
     # allocator (cudaMalloc of the 8 GB ray store, image and hit buffers) and page the library in

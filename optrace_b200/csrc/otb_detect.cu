@@ -25,7 +25,18 @@ struct DetArgs {
 
 #define OTB_DET_COARSE 8      // coarse samples of the two-level section search: covers nt <= 32
 
-__global__ void __launch_bounds__(128, 6) detector_hits_kernel(const DetArgs a)
+#ifndef OTB_DET_THREADS
+#define OTB_DET_THREADS 128
+#endif
+#ifndef OTB_DET_RESIDENT
+#define OTB_DET_RESIDENT 768      // resident threads per SM the register allocation is made for
+#endif
+#ifdef OTB_DET_PLAINLD
+#define OTB_DET_LD(p) (*(p))
+#else
+#define OTB_DET_LD(p) __ldcs(p)
+#endif
+__global__ void __launch_bounds__(OTB_DET_THREADS, OTB_DET_RESIDENT/OTB_DET_THREADS) detector_hits_kernel(const DetArgs a)
 {
     const int64_t N = a.st.N;
     const int nt = a.st.nt;
@@ -50,9 +61,18 @@ __global__ void __launch_bounds__(128, 6) detector_hits_kernel(const DetArgs a)
         // with two loads instead of the search over the sections below.
         double z_prev = 0.0, z_last = 0.0;
         bool last_section = false;
+        // ... and everything the hit of that section needs (both end points and the weight: 7 independent loads, the
+        // same bytes the walk below would read in three DEPENDENT round trips — the kernel is bound by DRAM latency)
+        // is requested in the same batch.
+        V3 pa = v3(0, 0, 0), pb = v3(0, 0, 0);
+        float wa = 0.0f;
         if (monotone && nt >= 2) {
-            z_prev = __ldcs(Pz + N*(int64_t)(nt - 2));
-            z_last = __ldcs(Pz + N*(int64_t)(nt - 1));
+            const int64_t oa = ray + N*(int64_t)(nt - 2), ob = ray + N*(int64_t)(nt - 1);
+            pa = v3(OTB_DET_LD(P + oa), OTB_DET_LD(P + oa + Nnt), OTB_DET_LD(P + oa + 2*Nnt));
+            pb = v3(OTB_DET_LD(P + ob), OTB_DET_LD(P + ob + Nnt), OTB_DET_LD(P + ob + 2*Nnt));
+            wa = OTB_DET_LD(Wt + oa);
+            z_prev = pa.z;
+            z_last = pb.z;
             last_section = z_prev < S.z_min;
         }
         if (last_section) {
@@ -66,8 +86,8 @@ __global__ void __launch_bounds__(128, 6) detector_hits_kernel(const DetArgs a)
             // sections inside the bracket that contains the first z >= z_min
             double zc[OTB_DET_COARSE + 1];
 #pragma unroll
-            for (int u = 0; u < OTB_DET_COARSE; ++u) zc[u] = (4*u < nt) ? __ldcs(Pz + N*(int64_t)(4*u)) : INFINITY;
-            const double zl = __ldcs(Pz + N*(int64_t)(nt - 1));
+            for (int u = 0; u < OTB_DET_COARSE; ++u) zc[u] = (4*u < nt) ? OTB_DET_LD(Pz + N*(int64_t)(4*u)) : INFINITY;
+            const double zl = OTB_DET_LD(Pz + N*(int64_t)(nt - 1));
             const double z0 = zc[0];
             no_start = (z0 >= S.z_min) && (z0 >= S.z_max);
             no_reach = !(zl >= S.z_min) && !(zl >= S.z_max);
@@ -79,7 +99,7 @@ __global__ void __launch_bounds__(128, 6) detector_hits_kernel(const DetArgs a)
                 const int j0 = 4*kb;                   // z[j0] < z_min, first_ge in (j0, min(j0 + 4, nt - 1)]
                 double zf[3];
 #pragma unroll
-                for (int u = 0; u < 3; ++u) zf[u] = (j0 + 1 + u < nt) ? __ldcs(Pz + N*(int64_t)(j0 + 1 + u)) : INFINITY;
+                for (int u = 0; u < 3; ++u) zf[u] = (j0 + 1 + u < nt) ? OTB_DET_LD(Pz + N*(int64_t)(j0 + 1 + u)) : INFINITY;
                 first_ge = (j0 + 4 < nt - 1) ? j0 + 4 : nt - 1;
 #pragma unroll
                 for (int u = 2; u >= 0; --u) if (j0 + 1 + u < nt && zf[u] >= S.z_min) first_ge = j0 + 1 + u;
@@ -90,7 +110,7 @@ __global__ void __launch_bounds__(128, 6) detector_hits_kernel(const DetArgs a)
             for (; j + 4 <= nt; j += 4) {
                 double z[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) z[u] = __ldcs(Pz + N*(int64_t)(j + u));
+                for (int u = 0; u < 4; ++u) z[u] = OTB_DET_LD(Pz + N*(int64_t)(j + u));
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const bool bmin = z[u] >= S.z_min, bmax = z[u] >= S.z_max;
@@ -100,7 +120,7 @@ __global__ void __launch_bounds__(128, 6) detector_hits_kernel(const DetArgs a)
                 }
             }
             for (; j < nt; ++j) {
-                const double z = __ldcs(Pz + N*(int64_t)j);
+                const double z = OTB_DET_LD(Pz + N*(int64_t)j);
                 const bool bmin = z >= S.z_min, bmax = z >= S.z_max;
                 no_start = no_start && (bmin && bmax);
                 no_reach = no_reach && (!bmin && !bmax);
@@ -118,17 +138,19 @@ __global__ void __launch_bounds__(128, 6) detector_hits_kernel(const DetArgs a)
                 // rays_by_mask (ray_storage.py:235-293): direction from position differences, normalised
                 const int s1 = (sec < nt - 1) ? sec + 1 : sec;
                 const int64_t o0 = ray + N*(int64_t)sec, o1 = ray + N*(int64_t)s1;
-                const V3 p = v3(P[o0], P[o0 + Nnt], P[o0 + 2*Nnt]);
-                const V3 s = unit3(v3(P[o1] - p.x, P[o1 + Nnt] - p.y, P[o1 + 2*Nnt] - p.z));
-                w = Wt[o0];
+                const bool pre = last_section && sec == nt - 2;        // the preloaded section
+                const V3 p = pre ? pa : v3(P[o0], P[o0 + Nnt], P[o0 + 2*Nnt]);
+                const V3 q = pre ? pb : v3(P[o1], P[o1 + Nnt], P[o1 + 2*Nnt]);
+                const V3 s = unit3(v3(q.x - p.x, q.y - p.y, q.z - p.z));
+                w = pre ? wa : Wt[o0];
                 ++sec;
                 if (sec >= nt) {          // ray ends at the outline: no intersection (raytracer.py:970-978)
                     w = 0.0f;
                     break;
                 }
-                h = surf_find_hit<OTB_CAPS_FULL>(S, nullptr, p, s, a.status);
+                h = surf_find_hit<OTB_CAPS_DET>(S, nullptr, p, s, a.status);
                 ill = ill || h.ill;
-                const double p2z = P[ray + N*(int64_t)sec + 2*Nnt];
+                const double p2z = pre ? pb.z : P[ray + N*(int64_t)sec + 2*Nnt];
                 more = h.p.z > p2z + OTB_C_EPS;      // hit behind the next stored point -> try next section
             }
             if (h.hit && w > 0.0f) {
@@ -149,7 +171,7 @@ __global__ void __launch_bounds__(128, 6) detector_hits_kernel(const DetArgs a)
     }
 
     // block reduction of the hit range (auto extent, raytracer.py:1042-1046) and the ill counter
-    __shared__ double smin_x[4], smax_x[4], smin_y[4], smax_y[4];
+    __shared__ double smin_x[OTB_DET_THREADS/32], smax_x[OTB_DET_THREADS/32], smin_y[OTB_DET_THREADS/32], smax_y[OTB_DET_THREADS/32];
     __shared__ int sill;
     if (threadIdx.x == 0) sill = 0;
     double mnx = ok ? X : INFINITY, mxx = ok ? X : -INFINITY, mny = ok ? Y : INFINITY, mxy = ok ? Y : -INFINITY;
@@ -173,12 +195,14 @@ __global__ void __launch_bounds__(128, 6) detector_hits_kernel(const DetArgs a)
             mny = fmin(smin_y[0], smin_y[k]); smin_y[0] = mny;
             mxy = fmax(smax_y[0], smax_y[k]); smax_y[0] = mxy;
         }
+#ifndef OTB_DET_NORANGE
         if (smin_x[0] <= smax_x[0]) {
             atomic_min_double(&a.range[0], smin_x[0]);
             atomic_max_double(&a.range[1], smax_x[0]);
             atomic_min_double(&a.range[2], smin_y[0]);
             atomic_max_double(&a.range[3], smax_y[0]);
         }
+#endif
         if (sill) atomicAdd(a.ill, (unsigned long long)sill);
     }
 }
@@ -331,7 +355,7 @@ int otb_detector_hits(const OtbRayStore* store, int64_t ray_begin, int64_t ray_e
     a.range = range_d;
     a.ill = (unsigned long long*)ill_d;
     a.status = status_d;
-    detector_hits_kernel<<<(unsigned)((n + 127)/128), 128, 0, st>>>(a);
+    detector_hits_kernel<<<(unsigned)((n + OTB_DET_THREADS - 1)/OTB_DET_THREADS), OTB_DET_THREADS, 0, st>>>(a);
     OTB_CUDA(cudaGetLastError());
     return OTB_OK;
 }

@@ -97,7 +97,7 @@ __device__ __forceinline__ void render_step(const KScene& sc, const RenderArgs& 
         bool ok = false;
         double X = 0.0, Y = 0.0;
         if ((active >> d) & 1u) {
-            HitResult h = surf_find_hit<CAPS>(rd.surf, nullptr, p_i, sd, a.status);
+            HitResult h = surf_find_hit<(CAPS == OTB_CAPS_LENS ? OTB_CAPS_LENS : OTB_CAPS_DET)>(rd.surf, nullptr, p_i, sd, a.status);
             if (!(h.p.z > r.p.z + OTB_C_EPS)) {           // else: hit behind the next stored point, next section
                 dm.finished |= 1u << d;
                 if (h.hit && w_i > 0.0f) {

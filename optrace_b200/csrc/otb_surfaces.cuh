@@ -9,6 +9,8 @@
 // fewer registers, a third of the code size (see profiles/).
 #define OTB_CAPS_LENS 0     // flat kinds + conic/sphere
 #define OTB_CAPS_FULL 1     // + tilted, asphere, function, data surfaces
+#define OTB_CAPS_DET 2      // flat kinds + conic + tilted: what a DETECTOR surface can be (detector.py:37-41); fully inlined
+                            // code without the out-of-line height functions (calls cost the detector kernels their registers)
 
 struct HitResult {
     V3 p;
@@ -269,13 +271,7 @@ __device__ __forceinline__ double surf_values_body(const KSurface& S, const doub
 {
     if (S.flags & OTB_SF_FLAT) return S.z_max;
     if (CAPS == OTB_CAPS_LENS && S.kind != OTB_SURF_CONIC) return S.z_max;
-    if (CAPS == OTB_CAPS_LENS) {
-        if (surf_mask(S, x, y)) return S.pos[2] + conic_values_rel(S, x - S.pos[0], y - S.pos[1]);
-        if (S.flags & OTB_SF_ROTSYM) return S.pos[2] + S.par[OTB_P_EDGEZ];
-        double r = S.r - OTB_N_EPS;
-        double phi = atan2(y - S.pos[1], x - S.pos[0]);
-        return S.pos[2] + conic_values_rel(S, r*cos(phi), r*sin(phi));
-    }
+    if (CAPS == OTB_CAPS_DET && S.kind != OTB_SURF_CONIC && S.kind != OTB_SURF_TILTED) return S.z_max;
     double xe = x - S.pos[0], ye = y - S.pos[1];
     if (!surf_mask(S, x, y)) {
         if (S.flags & OTB_SF_ROTSYM) return S.pos[2] + S.par[OTB_P_EDGEZ];
@@ -284,7 +280,11 @@ __device__ __forceinline__ double surf_values_body(const KSurface& S, const doub
         xe = r*cos(phi);
         ye = r*sin(phi);
     }
-    return S.pos[2] + surf_values_rel_body(S, aux, xe, ye);      // ONE inlined copy of the height switch in here
+    // ONE inlined copy of the height expression(s) in here
+    if (CAPS == OTB_CAPS_LENS) return S.pos[2] + conic_values_rel(S, xe, ye);
+    if (CAPS == OTB_CAPS_DET)
+        return S.pos[2] + ((S.kind == OTB_SURF_TILTED) ? xe*S.par[OTB_P_MX] + ye*S.par[OTB_P_MY] : conic_values_rel(S, xe, ye));
+    return S.pos[2] + surf_values_rel_body(S, aux, xe, ye);
 }
 static __device__ __noinline__ double surf_values_full(const KSurface* S, const double* aux, double x, double y)
 {
@@ -548,7 +548,7 @@ __device__ inline HitResult surf_find_hit(const KSurface& S, const double* __res
 {
     if (HOT) return find_hit_numeric<CAPS, 1>(S, aux, p, s, status);
     if (S.kind == OTB_SURF_CONIC) return find_hit_conic(S, p, s);
-    const bool tilted = (CAPS == OTB_CAPS_FULL) && S.kind == OTB_SURF_TILTED;
+    const bool tilted = (CAPS != OTB_CAPS_LENS) && S.kind == OTB_SURF_TILTED;
     HitResult h;
     h.hit = false;
     if (tilted) {

@@ -378,6 +378,7 @@ def run_gpu(args):
         this function returns"""
         nonlocal h2d, prev
         RT.upload_every_trace = True          # scene record + sampling tables travel host -> device every step
+        RT.deferred_status = True             # status word / message counters are collected at detector_image's own sync
         RT.trace(N_total)
         im = RT.detector_image()
         if rank == 0:       # the all-reduced image is identical on every rank: a job reads it back once
@@ -468,7 +469,8 @@ def run_gpu(args):
             "e2e": {"value": units/(e2e_ms*1e-3), "unit": "ray*surface/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h_bytes,
                     "image_bytes_dense": int(out.nbytes),
-                    "pipelining": "image download of step k overlaps the trace of step k+1 (depth 1); only the occupied "
+                    "pipelining": "Raytracer.deferred_status: one host synchronisation per step (after the detector hit search); "
+                                  "image download of step k overlaps the trace of step k+1 (depth 1); only the occupied "
                                   "32 x 32 tiles of the histogram travel (otb_tiles.cu), over NVLink and over PCIe; "
                                   "N > 1: the all-reduced image is read back on rank 0"},
             "gpu_launches": 8*args.steps,     # generate, trace_store, detector_hits, render x (resident + e2e region)

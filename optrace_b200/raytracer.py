@@ -41,6 +41,12 @@ class Raytracer(Group):
     upload_every_trace: bool = False
     """re-send scene and sampling tables host -> device on every trace even when unchanged (used by bench.py's
     end-to-end measurement, whose timed region must contain the host -> device copy of the step's inputs)"""
+    deferred_status: bool = False
+    """extension: trace() / trace_rays() return as soon as the kernels are queued instead of waiting for the device
+    status word and the message counters (the one host synchronisation of a trace).  Both are collected by the next
+    call that synchronises anyway — detector_image / detector_spectrum after their hit search, the next trace,
+    source_image, focus_search — or by finish_trace(); a device-side error (hit-finding timeout, n < 1, ...) is
+    raised there.  Default False: errors and messages appear inside trace() like in the reference."""
     use_specialised_kernels: bool = True
     arithmetic: str = "exact"
     """floating-point contract of the lens-surface step on the device.  "exact" (default): every + - * / sqrt rounds
@@ -461,6 +467,7 @@ class Raytracer(Group):
     # -- trace -----------------------------------------------------------------------------------------
     def trace(self, N: int) -> None:
         """Raytracer.trace (raytracer.py:262-415): N rays, generated and traced on the GPU(s)."""
+        self.finish_trace()
         if self._pretrace_check(N):
             return
         engine.ensure_init()
@@ -488,6 +495,7 @@ class Raytracer(Group):
         identical bundles.  `sharded`: under torchrun every rank passes the SAME global bundle
         and traces its contiguous share of it (dist.shard_range), like trace(N) does with generated rays."""
         N = int(p.shape[0])
+        self.finish_trace()
         if self._pretrace_check(N):
             return
         engine.ensure_init()
@@ -515,12 +523,24 @@ class Raytracer(Group):
             status = status | gen_status
         # the one collective and the one host synchronisation of a trace: message counters summed, status words
         # OR-ed over all ranks, so that every rank raises the same exception
-        self._msgs, st = dist.reduce_msgs_status(msgs, status)
-        engine.raise_status(st)
+        self._pending_trace = (msgs, status, N_global)
+        if not self.deferred_status:
+            self.finish_trace()
         self.rays = RayStorage()
         self.rays._attach(store, self.ray_sources, N_list, self.no_pol, N_global, begin)
-        self._show_messages(N_global)
         self._last_trace_snapshot = self.tracing_snapshot(self._scene_key)     # flattened once per trace
+
+    def finish_trace(self) -> None:
+        """collect the status word and the message counters of the last trace (see `deferred_status`); a no-op when
+        that has happened already"""
+        pend = self.__dict__.get("_pending_trace")
+        if pend is None:
+            return
+        self._pending_trace = None
+        msgs, status, N_global = pend
+        self._msgs, st = dist.reduce_msgs_status(msgs, status)
+        engine.raise_status(st)
+        self._show_messages(N_global)
 
     # -- detector ----------------------------------------------------------------------------------------
     def _check_detector_call(self, detector_index, source_index):
@@ -550,6 +570,7 @@ class Raytracer(Group):
         # hit range (MIN / MAX), ill-conditioned count (SUM) and status (OR) of all ranks: one all-gather of the
         # 48-byte record and the one host synchronisation of this call, reduced on the host
         r, ill_count, st = engine.read_det_meta(meta)
+        self.finish_trace()            # deferred status of the trace: the device has just been synchronised
         if extent is not None:
             extent_out = np.asarray_chkfinite(np.array(extent, dtype=np.float64))
         else:
@@ -605,6 +626,7 @@ class Raytracer(Group):
 
     def source_image(self, source_index: int = 0, limit: float = None, **kwargs) -> RenderImage:
         """Raytracer.source_image (raytracer.py:1331-1352)"""
+        self.finish_trace()
         if not self.ray_sources:
             raise RuntimeError("Ray Sources Missing.")
         if not self.rays.N_global:
@@ -634,6 +656,7 @@ class Raytracer(Group):
 
     def source_spectrum(self, source_index: int = 0, **kwargs) -> LightSpectrum:
         """Raytracer.source_spectrum (raytracer.py:1311-1329), binned on the device like detector_spectrum"""
+        self.finish_trace()
         if not self.ray_sources:
             raise RuntimeError("Ray Sources Missing.")
         if not self.rays.N_global:
@@ -690,6 +713,7 @@ class Raytracer(Group):
         optimisers are the reference's; every pass over the rays (section selection, weighted moments, cost images)
         runs on the device (otb_focus_prepare / otb_focus_moments / otb_focus_image)."""
         import scipy.optimize
+        self.finish_trace()
         if not (self.outline[4] <= z_start <= self.outline[5]):
             raise ValueError(f"Starting position z_start={z_start} outside raytracer z-outline range {self.outline[4:]}.")
         if method not in self.focus_search_methods:
@@ -769,6 +793,7 @@ class Raytracer(Group):
     def iterative_render(self, N, detector_index=0, limit=None, projection_method="Equidistant", pos=None, extent=None):
         if not self.ray_sources:
             raise RuntimeError("Ray Source(s) Missing.")
+        self.finish_trace()
         if not self.detectors:
             raise RuntimeError("Detector(s) Missing.")
         if (N := int(N)) <= 0:

@@ -246,3 +246,31 @@ def test_relaxed_arithmetic_error_level(ot):
     assert np.array_equal(RT._msgs, g["msgs"])
     RT, g = _trace_fixture(ot, "double_gauss", "relaxed")               # sources at 50 m
     assert gu.vecrel(RT.rays.p_list, g["p_list"]) < 5e-9 and np.array_equal(RT._msgs, g["msgs"])
+
+
+def test_deferred_status_collects_messages_at_the_detector_call(ot):
+    """Raytracer.deferred_status (extension): trace() returns without the host synchronisation; the message counters
+    and the device status arrive with the next synchronising call and equal those of an ordinary trace; a device-side
+    error is raised there instead of inside trace()"""
+    g = gu.load("double_gauss")
+    p0, s0, pol0, w0, wl, hz = gu.bundle(g)
+    RT = scenes.SCENES["double_gauss"](ot)
+    RT.trace_rays(p0, s0, pol0, w0, wl, N_list=g["N_list"])
+    msgs_ref = RT._msgs.copy()
+    assert msgs_ref.any()
+    img_ref = RT.detector_image()
+    RT2 = scenes.SCENES["double_gauss"](ot)
+    RT2.deferred_status = True
+    RT2.trace_rays(p0, s0, pol0, w0, wl, N_list=g["N_list"])
+    assert RT2.__dict__.get("_pending_trace") is not None          # nothing read back yet
+    img = RT2.detector_image()
+    assert RT2.__dict__.get("_pending_trace") is None
+    assert np.array_equal(RT2._msgs, msgs_ref)
+    assert np.array_equal(img.counts, img_ref.counts)
+    # a device-side error (generated direction with s_z <= 0, ray_source.py:353) is raised by finish_trace()
+    RT3 = ot.Raytracer(outline=[-10, 10, -10, 10, -10, 10])
+    RT3.add(ot.RaySource(ot.Point(), divergence="Isotropic", div_angle=80, s=[1, 0, 0.2]))
+    RT3.deferred_status = True
+    RT3.trace(10000)                   # returns
+    with pytest.raises(RuntimeError):
+        RT3.finish_trace()

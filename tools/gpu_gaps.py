@@ -20,6 +20,7 @@ prev = None
 def step():
     global prev
     RT.upload_every_trace = mode == "e2e"
+    RT.deferred_status = mode == "e2e"
     RT.trace(N)
     im = RT.detector_image()
     if mode == "e2e":

@@ -98,7 +98,7 @@ __device__ __forceinline__ void hurb_props(const KSurface& S, double x, double y
 // za, zb: standard normal deviates for HURB (only read when the step bends rays).
 // HOT = 1: lens front / back at a non-flat asphere / function / data surface only (the inlined numeric-surface step of
 // trace_step); everything else of the step is compiled out.
-template <bool POL, int CAPS, int HOT = 0>
+template <bool POL, int CAPS, int HOT = 0, int KIND = -1>
 __device__ __forceinline__ void trace_step_full(const KScene& sc, const double* __restrict__ aux, const OtbStep& st, RayState& r,
                                                 StepFlags& fl, double za, double zb, int* status)
 {
@@ -113,7 +113,7 @@ __device__ __forceinline__ void trace_step_full(const KScene& sc, const double* 
     bool hit = false;
 
     if (hw) {
-        HitResult h = surf_find_hit<CAPS, HOT>(S, aux, r.p, r.s, status);
+        HitResult h = surf_find_hit<CAPS, HOT, KIND>(S, aux, r.p, r.s, status);
         p_n = h.p;
         hit = h.hit;
         fl.ill = h.ill;
@@ -143,7 +143,7 @@ __device__ __forceinline__ void trace_step_full(const KScene& sc, const double* 
                 compute_polarization<POL>(s0, r.s, r.pol, pol_n, a, b);
             } else {
                 // Raytracer.__refraction (raytracer.py:761-829)
-                const V3 nrm = surf_normal<CAPS, HOT>(S, aux, p_n.x, p_n.y);
+                const V3 nrm = surf_normal<CAPS, HOT, KIND>(S, aux, p_n.x, p_n.y);
                 const double n1 = r.n;
                 const double ns = dot3(nrm, r.s);
                 const double N = n1/n2;
@@ -246,9 +246,10 @@ __device__ __noinline__ StepIO trace_step_slow(const KScene* sc, const double* a
 // the full step per ray; everything else runs the full step.  With OTB_STEP_OOL the full step exists only as
 // the out-of-line copy: the step loop then holds the straight-line path and ONE call site, which keeps the
 // loop-carried ray state in fixed registers (no copies where the paths merge) and the hot loop small.
+// func_spec (store-mode trace kernel only): function surfaces take the kind-specialised copy of the numeric step
 template <bool POL, int CAPS>
 __device__ __forceinline__ void trace_step(const KScene& sc, const double* __restrict__ aux, const OtbStep& st, RayState& r,
-                                           StepFlags& fl, double za, double zb, int* status)
+                                           StepFlags& fl, double za, double zb, int* status, const bool func_spec = false)
 {
     // A warp whose 32 rays are all absorbed (w == 0) has nothing to intersect or refract: dead rays repeat their
     // position, polarisation and zero weight in every later section (raytracer.py:309-312) and only follow the media
@@ -283,7 +284,13 @@ __device__ __forceinline__ void trace_step(const KScene& sc, const double* __res
                && (S.kind == OTB_SURF_FUNC || S.kind == OTB_SURF_DATA || S.kind == OTB_SURF_ASPHERE)) {
         // numeric surfaces: for them the full step IS the hot path — inlined here (scene in the constant bank, no
         // call per height evaluation) with everything but the lens branch compiled out
-        trace_step_full<POL, CAPS, 1>(sc, aux, st, r, fl, za, zb, status);
+        // ... and one copy per surface kind: the kind switches fold and the surface parameters stay in registers
+        // across the Illinois iterations instead of being re-read from the constant bank
+        // The specialised copy exists for function surfaces and is taken only in scenes whose numeric surfaces are ALL
+        // function surfaces (func_spec, decided once per kernel): cosine_surfaces 7.6 -> 6.7 ms; in a scene that mixes
+        // kinds every additional copy in use costs instruction-cache hits (zoo_numeric 89 -> 125 ms when used there).
+        if (func_spec && S.kind == OTB_SURF_FUNC) trace_step_full<POL, CAPS, 1, OTB_SURF_FUNC>(sc, aux, st, r, fl, za, zb, status);
+        else trace_step_full<POL, CAPS, 1>(sc, aux, st, r, fl, za, zb, status);
         done = true;
     }
 #if OTB_STEP_OOL

@@ -158,10 +158,14 @@ __device__ __forceinline__ double polyval(const double* __restrict__ c, int n, d
 // RectangularSurface.mask (rectangular_surface.py:100-112), SlitSurface.mask (slit_surface.py:89-102),
 // FunctionSurface2D.mask (function_surface_2d.py:158-191).  Absolute coordinates.
 // ------------------------------------------------------------------------------------------------
+// KIND >= 0: the surface kind is a compile-time constant (the kind-specialised copies of the numeric lens step, see
+// trace_step): every kind switch folds and the loop-invariant surface parameters are hoisted out of the Illinois loop.
+template <int KIND = -1>
 __device__ inline bool surf_mask(const KSurface& S, double x, double y)
 {
     const double x0 = S.pos[0], y0 = S.pos[1];
-    switch (S.kind) {
+    const int kind = (KIND >= 0) ? KIND : S.kind;
+    switch (kind) {
     case OTB_SURF_RING: {
         double dx = x - x0, dy = y - y0;
         double r2 = dx*dx + dy*dy;
@@ -174,7 +178,7 @@ __device__ inline bool surf_mask(const KSurface& S, double x, double y)
         rot_rc(S, OTB_P_COSM, x - x0, y - y0, xr, yr);
         double xe = S.par[OTB_P_DIMX]/2, ye = S.par[OTB_P_DIMY]/2;
         bool m = (-xe - OTB_N_EPS <= xr) && (xr <= xe + OTB_N_EPS) && (-ye - OTB_N_EPS <= yr) && (yr <= ye + OTB_N_EPS);
-        if (S.kind == OTB_SURF_SLIT) {
+        if (kind == OTB_SURF_SLIT) {
             double xi = S.par[OTB_P_DIMIX]/2, yi = S.par[OTB_P_DIMIY]/2;
             bool inside = (-xi + OTB_N_EPS <= xr) && (xr <= xi - OTB_N_EPS) && (-yi + OTB_N_EPS <= yr) && (yr <= yi - OTB_N_EPS);
             m = m && !inside;
@@ -185,7 +189,7 @@ __device__ inline bool surf_mask(const KSurface& S, double x, double y)
         double dx = x - x0, dy = y - y0;
         double b = S.r + OTB_N_EPS;
         bool m = dx*dx + dy*dy <= b*b;
-        if (S.kind == OTB_SURF_FUNC && (S.flags & OTB_SF_HAS_MASK)) {
+        if (kind == OTB_SURF_FUNC && (S.flags & OTB_SF_HAS_MASK)) {
             int id = (int)S.par[OTB_P_FMASK];
             double mf;
             if (S.flags & OTB_SF_1D) {
@@ -213,9 +217,10 @@ __device__ __forceinline__ double conic_values_rel(const KSurface& S, double x, 
     return S.par[OTB_P_RHO]*r2/(1 + sqrt(1 - S.par[OTB_P_KP1RHO2]*r2));
 }
 
+template <int KIND = -1>
 __device__ __forceinline__ double surf_values_rel_body(const KSurface& S, const double* __restrict__ aux, double x, double y)
 {
-    switch (S.kind) {
+    switch ((KIND >= 0) ? KIND : S.kind) {
     case OTB_SURF_CONIC:
         return conic_values_rel(S, x, y);
     case OTB_SURF_TILTED:
@@ -266,14 +271,14 @@ __device__ __forceinline__ double surf_values_rel(const KSurface& S, const doubl
 }
 
 // Surface.values (surface.py:137-164): absolute height with the radially continued edge
-template <int CAPS>
+template <int CAPS, int KIND = -1>
 __device__ __forceinline__ double surf_values_body(const KSurface& S, const double* __restrict__ aux, double x, double y)
 {
     if (S.flags & OTB_SF_FLAT) return S.z_max;
     if (CAPS == OTB_CAPS_LENS && S.kind != OTB_SURF_CONIC) return S.z_max;
     if (CAPS == OTB_CAPS_DET && S.kind != OTB_SURF_CONIC && S.kind != OTB_SURF_TILTED) return S.z_max;
     double xe = x - S.pos[0], ye = y - S.pos[1];
-    if (!surf_mask(S, x, y)) {
+    if (!surf_mask<KIND>(S, x, y)) {
         if (S.flags & OTB_SF_ROTSYM) return S.pos[2] + S.par[OTB_P_EDGEZ];
         double r = S.r - OTB_N_EPS;
         double phi = atan2(ye, xe);
@@ -284,7 +289,7 @@ __device__ __forceinline__ double surf_values_body(const KSurface& S, const doub
     if (CAPS == OTB_CAPS_LENS) return S.pos[2] + conic_values_rel(S, xe, ye);
     if (CAPS == OTB_CAPS_DET)
         return S.pos[2] + ((S.kind == OTB_SURF_TILTED) ? xe*S.par[OTB_P_MX] + ye*S.par[OTB_P_MY] : conic_values_rel(S, xe, ye));
-    return S.pos[2] + surf_values_rel_body(S, aux, xe, ye);
+    return S.pos[2] + surf_values_rel_body<KIND>(S, aux, xe, ye);
 }
 static __device__ __noinline__ double surf_values_full(const KSurface* S, const double* aux, double x, double y)
 {
@@ -304,12 +309,12 @@ __device__ __forceinline__ double surf_values(const KSurface& S, const double* _
 // ------------------------------------------------------------------------------------------------
 // HOT = 1: the inlined instantiation of the numeric-surface lens step in the trace loop (asphere / function / data
 // surfaces only, see trace_step): no conic code, heights evaluated inline at ONE code site per loop.
-template <int CAPS, int HOT = 0>
+template <int CAPS, int HOT = 0, int KIND = -1>
 __device__ inline V3 surf_normal(const KSurface& S, const double* __restrict__ aux, double x, double y)
 {
-    const int k = S.kind;
+    const int k = (KIND >= 0) ? KIND : S.kind;
     if ((S.flags & OTB_SF_FLAT) && k != OTB_SURF_TILTED) return v3(0.0, 0.0, 1.0);
-    if (!surf_mask(S, x, y)) return v3(0.0, 0.0, 1.0);
+    if (!surf_mask<KIND>(S, x, y)) return v3(0.0, 0.0, 1.0);
     if (CAPS == OTB_CAPS_LENS && k != OTB_SURF_CONIC) return v3(0.0, 0.0, 1.0);
     const double x0 = S.pos[0], y0 = S.pos[1];
     const double dx = x - x0, dy = y - y0;
@@ -379,7 +384,7 @@ __device__ inline V3 surf_normal(const KSurface& S, const double* __restrict__ a
         for (int q = 0; q < 4; ++q) {
             const double xx = (q == 0) ? dx - eps : (q == 1) ? dx + eps : dx;
             const double yy = (q == 2) ? dy - eps : (q == 3) ? dy + eps : dy;
-            const double v = surf_values_rel_body(S, aux, xx, yy);
+            const double v = surf_values_rel_body<KIND>(S, aux, xx, yy);
             v0 = (q == 0) ? v : v0;
             v1 = (q == 1) ? v : v1;
             v2 = (q == 2) ? v : v2;
@@ -429,7 +434,7 @@ __device__ __forceinline__ void handle_abnormal(const KSurface& S, const double*
 // (:365-367) and the final deviation check of _find_hit_handle_abnormal (:452, whose argument is the last point
 // evaluated, so its height difference is the value already at hand) — same operations on the same operands as the
 // reference, a third of the code.
-template <int CAPS, int HOT = 0>
+template <int CAPS, int HOT = 0, int KIND = -1>
 __device__ inline HitResult find_hit_numeric(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
 {
     HitResult h;
@@ -460,7 +465,7 @@ __device__ inline HitResult find_hit_numeric(const KSurface& S, const double* __
     for (;;) {
         const double ts = (phase == 0) ? t1 : (phase == 1) ? t2 : t1 - f1/(f2 - f1)*(t2 - t1);
         const V3 pl = along(p, s, ts);
-        const double fts = pl.z - (HOT ? surf_values_body<CAPS>(S, aux, pl.x, pl.y) : surf_values<CAPS>(S, aux, pl.x, pl.y));
+        const double fts = pl.z - (HOT ? surf_values_body<CAPS, KIND>(S, aux, pl.x, pl.y) : surf_values<CAPS>(S, aux, pl.x, pl.y));
         if (phase == 0) {
             f1 = fts;
             h.p = pl;                 // kept when the bracket is degenerate (surface.py:352)
@@ -496,7 +501,7 @@ __device__ inline HitResult find_hit_numeric(const KSurface& S, const double* __
         }
         ++it;
     }
-    h.hit = surf_mask(S, h.p.x, h.p.y);
+    h.hit = surf_mask<KIND>(S, h.p.x, h.p.y);
     handle_abnormal_dz(S, p, s, h, dz);
     return h;
 }
@@ -543,10 +548,10 @@ __device__ inline HitResult find_hit_conic(const KSurface& S, const V3& p, const
 
 // TiltedSurface.find_hit (tilted_surface.py:91-123): analytic plane hit; rays that miss the disc go through the
 // numeric finder (radially continued edge).  Shares the ONE inlined copy of find_hit_numeric with the other kinds.
-template <int CAPS, int HOT = 0>
+template <int CAPS, int HOT = 0, int KIND = -1>
 __device__ inline HitResult surf_find_hit(const KSurface& S, const double* __restrict__ aux, const V3& p, const V3& s, int* status)
 {
-    if (HOT) return find_hit_numeric<CAPS, 1>(S, aux, p, s, status);
+    if (HOT) return find_hit_numeric<CAPS, 1, KIND>(S, aux, p, s, status);
     if (S.kind == OTB_SURF_CONIC) return find_hit_conic(S, p, s);
     const bool tilted = (CAPS != OTB_CAPS_LENS) && S.kind == OTB_SURF_TILTED;
     HitResult h;

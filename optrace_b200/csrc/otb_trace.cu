@@ -83,7 +83,7 @@ struct StoreCursor {
 // one sequential step: trace, book messages, store section i+1
 template <bool POL, int CAPS>
 __device__ __forceinline__ void store_step(const KScene& sc, const TraceArgs& a, const double* aux, const int i, RayState& r,
-                                           StoreCursor& c, int* smsgs, const bool valid, const int64_t rr)
+                                           StoreCursor& c, int* smsgs, const bool valid, const int64_t rr, const bool func_spec)
 {
     const int64_t N = a.out.N;
     const int nt = a.out.nt;
@@ -101,7 +101,7 @@ __device__ __forceinline__ void store_step(const KScene& sc, const TraceArgs& a,
     }
     StepFlags fl;
     const double z_prev = r.p.z;
-    trace_step<POL, CAPS>(sc, aux, st, r, fl, za, zb, a.status);
+    trace_step<POL, CAPS>(sc, aux, st, r, fl, za, zb, a.status, func_spec);
     c.z_decrease = c.z_decrease | (r.p.z < z_prev);
     book_step(smsgs, nt, i, valid, fl);
 
@@ -153,6 +153,14 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
     __syncthreads();
 
     const int64_t Nnt = N*(int64_t)nt;
+    // all numeric surfaces of the scene are function surfaces: they take their kind-specialised step (trace_step)
+    bool func_spec = (CAPS == OTB_CAPS_FULL);
+    if (CAPS == OTB_CAPS_FULL) {
+        for (int i = 0; i < sc.n_steps; ++i) {
+            const KSurface& S = sc.surf[sc.steps[i].surface];
+            if (!(S.flags & OTB_SF_FLAT) && (S.kind == OTB_SURF_DATA || S.kind == OTB_SURF_ASPHERE)) func_spec = false;
+        }
+    }
 
     for (int64_t base = a.k_begin + (int64_t)blockIdx.x*blockDim.x; base < a.k_end; base += (int64_t)gridDim.x*blockDim.x) {
         const int64_t ray = base + threadIdx.x;
@@ -217,11 +225,11 @@ trace_store_kernel(const __grid_constant__ TraceArgs a)
 #if OTB_SPEC
         // straight-line code: one inlined copy of store_step per literal step index, everything about the step
         // (role, surface kind and parameters, media) folds at compile time
-#define OTB_CALL_STORE_STEP(i) store_step<POL, CAPS>(sc, a, aux, i, r, cur, smsgs, valid, rr);
+#define OTB_CALL_STORE_STEP(i) store_step<POL, CAPS>(sc, a, aux, i, r, cur, smsgs, valid, rr, func_spec);
         OTB_SPEC_FOREACH_STEP(OTB_CALL_STORE_STEP)
 #else
         OTB_UNROLL_N(OTB_STEP_UNROLL)
-        for (int i = 0; i < sc.n_steps; ++i) store_step<POL, CAPS>(sc, a, aux, i, r, cur, smsgs, valid, rr);
+        for (int i = 0; i < sc.n_steps; ++i) store_step<POL, CAPS>(sc, a, aux, i, r, cur, smsgs, valid, rr, func_spec);
 #endif
         if (valid && cur.z_decrease) atomicOr(a.status, OTB_STATUS_Z_DECREASE);    // practically never
         if (valid) {

@@ -481,7 +481,7 @@ def run_gpu(args):
             v, dt, used, _, rays_cpu, kind, sample = reference_or_port(3, 1, 20.0)
             line["cpu_baseline"] = {"value": v, "unit": "ray*surface/s", "cores": used, "kind": kind, "sample": sample,
                                     "ms_per_surface_per_Mray": 1e9/v}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         td.destroy_process_group()
 

@@ -429,6 +429,7 @@ def run_gpu(args):
         # DRAM traffic of the trace kernel from the committed `ncu --set full` capture of this same workload
         # (profiles/, dram__bytes_read.sum + dram__bytes_write.sum per launch); only valid for the default size
         traffic = None
+        traffic_current = None
         profs = sorted((ROOT / "profiles").glob("r*_trace_store_final_ncu.csv"))      # newest round last
         prof = profs[-1] if profs else ROOT / "profiles" / "none"
         if prof.exists() and args.rays == RAYS_PER_GPU:
@@ -438,6 +439,9 @@ def run_gpu(args):
                     c = ln.split(",")
                     if c[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                         tb += float(c[2])*{"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[c[1]]
+                    if c[0] == "engine_source_digest":
+                        from optrace_b200 import build as _b
+                        traffic_current = c[2] == _b.source_digest()
                 traffic = tb or None
             except Exception:
                 traffic = None
@@ -463,6 +467,7 @@ def run_gpu(args):
                          "traffic": traffic,
                          "traffic_source": f"profiles/{prof.name} (ncu --set full capture of this kernel on this workload; "
                                            "includes the 68 B/ray bundle read)",
+                         "traffic_capture_matches_engine_sources": traffic_current,
                          "achieved_incl_bundle_read": (alg_bytes + bundle_bytes)/(kernel_ms*1e-3)/1e9,
                          "kernel": "trace_store_kernel<POL, LENS>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes},

@@ -7,6 +7,7 @@ import csv
 import re
 import subprocess
 import sys
+import pathlib
 
 KEEP = ("gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -56,6 +57,10 @@ def main():
         for nm, v in stalls.most_common():
             if v:
                 rows.append((f"pc_sampling.{nm}", "% of samples", f"{100*v/max(1, nsamp):.1f}"))
+    # digest of the engine sources this summary was made with: bench.py reports whether a capture is still current
+    sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
+    from optrace_b200 import build
+    rows.append(("engine_source_digest", "", build.source_digest()))
     with open(out, "w", newline="") as f:
         csv.writer(f).writerows(rows)
     print(f"wrote {out}: {len(rows)} rows")

@@ -9,7 +9,9 @@
 #include "otb_step.cuh"
 #include "otb_gen.cuh"
 
+#ifndef OTB_TRACE_THREADS
 #define OTB_TRACE_THREADS 128
+#endif
 // Scenes with numeric surfaces (CAPS_FULL) run ONE block of 512 threads per SM (16 warps at 128 registers; measured on
 // cosine_surfaces / zoo_numeric: 256 threads 11.2 / 120 ms, 384: 8.7 / 106, 448: 9.2 / 106, 512: 7.6 / 89, 640: 9.5 / 89,
 // 768: 10.5 / 91 ms per 10 M rays — the kernel is latency-bound, more warps help until the spills take over): the

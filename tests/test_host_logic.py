@@ -301,3 +301,35 @@ def test_balanced_source_shards_tile_every_source():
         N, nt = 40, 2
     rs._attach(_S2(), [None]*3, [40, 60, 10], False, 110, 30)
     assert rs._blocks == [(0, 30, 10), (1, 40, 30)] and rs.ray_begin == 30 and rs._local_range(1) == (10, 40)
+
+
+def test_reference_gaussian_filter_weights_depend_on_the_hosts_simd_level():
+    """Justifies golden_util.W_RTOL (deviation 1).  The reference evaluates a Gaussian
+    TransmissionSpectrum with numpy's FLOAT32 exp (spectrum.py:113 + NEP 50).  That loop is dispatched by CPU feature:
+    the AVX2/AVX512 kernels are accurate to ~2.5 ulp, the baseline loop calls libm's (practically correctly rounded)
+    expf.  The same reference therefore produces weights that differ by up to 2 float32 ulp (1.9e-7) between hosts,
+    so no engine can match it to 1e-9 on every host; the engine rounds a float64 exp once, which is what the
+    baseline loop gives in > 99.9 % of the arguments."""
+    import os
+    import subprocess
+    import sys
+    import numpy as np
+    try:
+        from numpy._core._multiarray_umath import __cpu_features__ as feats
+    except Exception:
+        pytest.skip("numpy CPU feature table not available")
+    simd = [k for k, v in feats.items() if v and (k.startswith("AVX") or k == "FMA3")]
+    if "AVX2" not in simd:
+        pytest.skip("this host already runs numpy's baseline float32 exp")
+    code = ("import numpy as np, sys; x = -(np.linspace(0, 30, 200001).astype(np.float32)); "
+            "sys.stdout.buffer.write(np.exp(x).tobytes())")
+    env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=" ".join(simd))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, check=True).stdout
+    base = np.frombuffer(out, dtype=np.float32)                       # numpy on a host without AVX
+    x = -(np.linspace(0, 30, 200001).astype(np.float32))
+    here = np.exp(x)                                                  # numpy on this host (SIMD loop)
+    engine_rule = np.exp(x.astype(np.float64)).astype(np.float32)    # float64 exp rounded once (otb_media.cuh)
+    rel = np.abs(here.astype(np.float64) - base)/base
+    assert (here != base).mean() > 0.05            # the reference's own numbers differ between the two hosts ...
+    assert 5e-8 < rel.max() < 3e-7                 # ... by up to ~2 float32 ulp: W_RTOL = 3e-7 covers exactly that
+    assert (engine_rule != base).mean() < 1e-2     # the engine's rule IS the baseline loop up to rare last-bit ties

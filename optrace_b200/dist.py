@@ -176,24 +176,51 @@ def allreduce_range_(rng):
 STATUS_BITS = 5      # OTB_STATUS_* bits of include/otb.h
 
 
-def reduce_msgs_status(msgs, status):
-    """Message counters (SUM) and the device status word (bitwise OR) of all ranks with ONE collective and ONE
-    host synchronisation: the status bits travel bit-expanded behind the counters (NCCL has no bitwise reduction),
-    so every rank raises the same exception instead of one rank raising while the others wait in the next
-    collective.  Returns (msgs ndarray like the input shape, status int)."""
+def reduce_msgs_status_begin(msgs, status):
+    """Message counters (SUM) and the device status word (bitwise OR) of all ranks with ONE collective: the status
+    bits travel bit-expanded behind the counters (NCCL has no bitwise reduction), so every rank raises the same
+    exception instead of one rank raising while the others wait in the next collective.  Enqueues the collective
+    and an asynchronous copy into pinned host memory on the current stream; reduce_msgs_status_end() waits for it —
+    with Raytracer.deferred_status that is after the next synchronisation point, at no extra cost."""
     import torch
     shape = tuple(msgs.shape)
-    if is_dist() and world() > 1:
+    multi = is_dist() and world() > 1
+    if multi:
         td = _td()
         bits = (status.to(torch.int64).reshape(1) >> torch.arange(STATUS_BITS, device=status.device)) & 1
         buf = torch.cat((msgs.reshape(-1).to(torch.int64), bits))
         td.all_reduce(buf, op=td.ReduceOp.SUM)
-        h = buf.cpu().numpy()
-        st = int(sum((1 << i) for i in range(STATUS_BITS) if h[-STATUS_BITS + i] > 0))
-        return h[:-STATUS_BITS].reshape(shape).astype(int), st
-    buf = torch.cat((msgs.reshape(-1).to(torch.int64), status.to(torch.int64).reshape(1)))
-    h = buf.cpu().numpy()
-    return h[:-1].reshape(shape).astype(int), int(h[-1])
+    else:
+        buf = torch.cat((msgs.reshape(-1).to(torch.int64), status.to(torch.int64).reshape(1)))
+    if not buf.is_cuda:          # gloo / CPU tensors (tests): nothing to overlap
+        return buf, None, shape, multi
+    from . import engine
+    h = engine.pinned_take(buf.shape, torch.int64)
+    h.copy_(buf, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    return h, ev, shape, multi
+
+
+def reduce_msgs_status_end(handle):
+    """(msgs ndarray like the input shape, status int) of a reduce_msgs_status_begin handle; one host wait"""
+    h, ev, shape, multi = handle
+    if ev is not None:
+        ev.synchronize()
+        a = h.numpy().copy()
+        from . import engine
+        engine.pinned_give(h)
+    else:
+        a = h.numpy()
+    if multi:
+        st = int(sum((1 << i) for i in range(STATUS_BITS) if a[-STATUS_BITS + i] > 0))
+        return a[:-STATUS_BITS].reshape(shape).astype(int), st
+    return a[:-1].reshape(shape).astype(int), int(a[-1])
+
+
+def reduce_msgs_status(msgs, status):
+    """both halves at once: ONE collective and ONE host synchronisation"""
+    return reduce_msgs_status_end(reduce_msgs_status_begin(msgs, status))
 
 
 def gather_rows(t):

@@ -523,7 +523,7 @@ class Raytracer(Group):
             status = status | gen_status
         # the one collective and the one host synchronisation of a trace: message counters summed, status words
         # OR-ed over all ranks, so that every rank raises the same exception
-        self._pending_trace = (msgs, status, N_global)
+        self._pending_trace = (dist.reduce_msgs_status_begin(msgs, status), N_global)
         if not self.deferred_status:
             self.finish_trace()
         self.rays = RayStorage()
@@ -537,8 +537,8 @@ class Raytracer(Group):
         if pend is None:
             return
         self._pending_trace = None
-        msgs, status, N_global = pend
-        self._msgs, st = dist.reduce_msgs_status(msgs, status)
+        handle, N_global = pend
+        self._msgs, st = dist.reduce_msgs_status_end(handle)
         engine.raise_status(st)
         self._show_messages(N_global)
 

@@ -272,5 +272,6 @@ def test_deferred_status_collects_messages_at_the_detector_call(ot):
     RT3.add(ot.RaySource(ot.Point(), divergence="Isotropic", div_angle=80, s=[1, 0, 0.2]))
     RT3.deferred_status = True
     RT3.trace(10000)                   # returns
+    assert RT3.__dict__.get("_pending_trace") is not None
     with pytest.raises(RuntimeError):
         RT3.finish_trace()

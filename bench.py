@@ -16,6 +16,7 @@ One "step" = one pass of the hot path over one batch: on-device ray generation (
              reference's own threading scheme (contiguous ray ranges per host thread) on a bounded sample.
 """
 import argparse
+import gc
 import json
 import os
 import pathlib
@@ -49,6 +50,8 @@ def parse():
                          "scene-specialised variant of Raytracer.compile()")
     ap.add_argument("--no-compare", action="store_true", help="skip timing the other engine build")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not run the nvidia-smi clock sampler")
+    ap.add_argument("--keep-gc", action="store_true", help="diagnostic: leave Python's cyclic garbage collector running in the timed regions")
+    ap.add_argument("--gc-log", action="store_true", help="diagnostic: report garbage collector pauses on stderr")
     return ap.parse_args()
 
 
@@ -317,18 +320,40 @@ def run_gpu(args):
         clocks.start()
     # burn-in before the W warm-up steps of the contract: on a fresh box the first steps still grow the caching
     # allocator (cudaMalloc of the 8 GB ray store, image and hit buffers) and page the library in
+    # (the returned image is HELD across the next step exactly like in the timed loop: otherwise the second image
+    # buffer of the steady state is first allocated — a synchronous cudaMalloc of 160 MB, 5-400 ms on these boxes —
+    # by the second timed step)
     for _ in range(max(0, 8 - args.warmup)):
-        step_resident(False)
+        img = step_resident(False)
     for _ in range(args.warmup):
-        step_resident(False)
+        img = step_resident(False)
     barrier()
     if rank == 0:
         clocks.wait_first()
         clocks.mark()
+    # A generation-2 pass of Python's cyclic garbage collector walks every object torch and numpy created at import
+    # (~1e6) and takes 50-100 ms: inside a 100 ms timed region it doubles ms_per_step (seen in one of four runs).
+    # Everything alive after the warm-up is moved to the permanent generation and the collector pauses while the
+    # steps are timed; the steps themselves create no reference cycles worth collecting.
+    gc_pauses = []
+    if args.gc_log:
+        _t = [0.0]
+        def _gc_cb(phase, info):
+            if phase == "start":
+                _t[0] = time.perf_counter()
+            else:
+                gc_pauses.append((info["generation"], (time.perf_counter() - _t[0])*1e3))
+        gc.callbacks.append(_gc_cb)
+    if not args.keep_gc:
+        gc.collect()
+        gc.freeze()
+        gc.disable()
     t0, t1 = ev(), ev()
     t0.record()
+    step_wall = []
     for _ in range(args.steps):
         img = step_resident(True)
+        step_wall.append(time.perf_counter())
     img._wait_device()       # N > 1: the side-stream all-reduce of the last image belongs to the timed region
     t1.record()
     barrier()
@@ -371,6 +396,7 @@ def run_gpu(args):
     del RT.check_if_rays_are_current
     h2d = 0
     prev = None
+    phases = []        # diagnostics (--gc-log): host time per phase [trace, materialise(prev), detector_image, download_async]
 
     def step_e2e():
         """one step through the public API; the image download (RenderImage.download_async, pinned staging,
@@ -379,33 +405,58 @@ def run_gpu(args):
         nonlocal h2d, prev
         RT.upload_every_trace = True          # scene record + sampling tables travel host -> device every step
         RT.deferred_status = True             # status word / message counters are collected at detector_image's own sync
-        RT.trace(N_total)
-        im = RT.detector_image()
-        if rank == 0:       # the all-reduced image is identical on every rank: a job reads it back once
-            im.download_async()
+        tp = [time.perf_counter()]
+        RT.trace(N_total)                     # returns as soon as generator and trace kernel are queued
+        tp.append(time.perf_counter())
         # bytes sent per step: kernel-parameter scene (KScene, ~30 KB), aux tables, generator tables
         h2d = 30648 + RT._scene.flat.aux.nbytes + int(RT._gen_cache[2].numel())*8
+        # the previous step's image is completed on the host while this step's trace runs on the device
         out = None
-        if prev is not None:
-            out = prev._materialise() if rank == 0 else prev._wait_device()
+        if prev is not None and rank == 0:
+            out = prev._materialise()
+        tp.append(time.perf_counter())
+        im = RT.detector_image()
+        tp.append(time.perf_counter())
+        if rank == 0:       # the all-reduced image is identical on every rank: a job reads it back once
+            im.download_async()
+        elif prev is not None:
+            prev._wait_device()               # other ranks: the reduced image is complete on the device
+        tp.append(time.perf_counter())
+        phases.append(np.diff(np.array(tp))*1e3)
         prev = im
         return out
 
-    for _ in range(max(3, args.warmup)):      # >= 3: two pinned staging buffers are page-locked on first use
+    # >= 6 untimed steps, and the pipeline is NOT drained before the timed loop: the caching allocator hands the 8 GB ray
+    # store, the 680 MB bundle and the image buffers out of the same large blocks, and any change of the set of live
+    # tensors (a drained pipeline, the switch from the resident loop above) makes one of the next traces pay a
+    # synchronous cudaMalloc of several GB (8-95 ms, seen at the third timed step in 4 of 10 runs).  The first timed
+    # step therefore also completes the last warm-up image: one materialise more than steps, none less.
+    for _ in range(max(6, args.warmup)):
         step_e2e()
-    prev._materialise() if rank == 0 else prev._wait_device()
-    prev = None
     barrier()
     w0 = time.perf_counter()
     t0.record()
+    e2e_wall = []
+    phases.clear()
     for _ in range(args.steps):
         step_e2e()
+        e2e_wall.append(time.perf_counter())
     # the last image is on the host (rank 0) / complete on the device (other ranks) inside the timed region as well
     out = prev._materialise() if rank == 0 else prev._wait_device()
     d2h_bytes = int(prev.transferred_bytes) if rank == 0 else 0
     t1.record()
     barrier()
     e2e_ms = max(t0.elapsed_time(t1), (time.perf_counter() - w0)*1e3)/args.steps
+    gc.enable()
+    if args.gc_log and rank == 0:
+        d = np.diff(np.array(step_wall))*1e3
+        print(f"[bench] host time between the returns of consecutive resident steps (ms): {np.round(d, 2).tolist()}", file=sys.stderr)
+        d = np.diff(np.array(e2e_wall))*1e3
+        print(f"[bench] host time between the returns of consecutive e2e steps (ms): {np.round(d, 2).tolist()}", file=sys.stderr)
+        k = int(np.argmax(d)) + 1
+        print(f"[bench] e2e phases [trace, materialise(prev), detector_image, download_async] of step {k} (ms): "
+              f"{np.round(phases[k], 2).tolist()}; of step {k + 3}: {np.round(phases[min(k + 3, len(phases) - 1)], 2).tolist()}", file=sys.stderr)
+        print(f"[bench] garbage collector passes (generation, ms): {[(g, round(t, 2)) for g, t in gc_pauses if t > 0.2]}", file=sys.stderr)
     clk = clocks.stop() if rank == 0 else None
 
     # max over ranks

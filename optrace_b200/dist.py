@@ -256,14 +256,23 @@ def broadcast_ints(a: np.ndarray, device) -> np.ndarray:
     return np.asarray(a, dtype=np.int64)
 
 
+_split_cache = None
+
+
 def shared_split(N: int, powers, device) -> np.ndarray:
     """rays per source, identical on every rank (RayStorage.init, ray_storage.py:56-68).  The split is deterministic
     unless N does not divide by the power ratios: only then the remainder is drawn with np.random.choice and rank
     0's draw is broadcast (a collective plus a host synchronisation that the common case does not pay)."""
     from .ray_storage import split_rays
+    global _split_cache
+    key = (int(N), tuple(float(p) for p in powers))
+    if _split_cache is not None and _split_cache[0] == key:      # deterministic case only (see below)
+        return _split_cache[1].copy()
     P = np.asarray(powers, dtype=np.float64)
     if N - int(np.sum((N*P/np.sum(P)).astype(int))) == 0:
-        return split_rays(N, powers)
+        out = split_rays(N, powers)
+        _split_cache = (key, out.copy())
+        return out
     return broadcast_ints(split_rays(N, powers), device)
 
 

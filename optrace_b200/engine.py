@@ -634,6 +634,18 @@ def assemble_submit(shape, ready_event, hdr_t, buf_t):
     return _assembler.submit(task)
 
 
+def release_dense_async(token) -> None:
+    """release_dense on the assembler thread (a RenderImage usually dies on the caller's critical path, right before
+    the next trace is queued); falls back to the caller's thread when the worker does not exist (yet)"""
+    if _assembler is None:
+        release_dense(token)
+        return
+    try:
+        _assembler.submit(release_dense, token)
+    except RuntimeError:          # interpreter shutting down
+        release_dense(token)
+
+
 def release_dense(token) -> None:
     """give a padded host image back to the pool (called when its RenderImage dies): the written tiles are zeroed"""
     out, ids = token

@@ -317,7 +317,7 @@ class RenderImage:
                 from . import engine
                 self._data = None
                 self._dense_token = None
-                engine.release_dense(tok)
+                engine.release_dense_async(tok)      # clearing the written tiles: worker thread
             if self._host_buf is not None:
                 from . import engine
                 if self._host_ready is not None:

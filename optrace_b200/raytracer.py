@@ -384,8 +384,15 @@ class Raytracer(Group):
         """OtbSource array of the local blocks (source, global first ray id, count) + the table buffer on the device"""
         recs, aux_d = self._generator_tables()          # (re-)upload of the sampling tables on the current stream
         sl = blocks
-        arr = (_cabi.OtbSource*max(len(sl), 1))()
         fids = scene.flat.source_func_ids
+        coherent = int(bool(self.coherent_bundles) and scene_caps_lean(scene))
+        # the records are plain host structures: rebuilt only when something they are made of changed (a repeated
+        # trace of the same scene re-sends the device tables above, not this loop of ~40 field assignments per source)
+        key = (self._gen_cache[0], tuple(int(v) for v in N_list), tuple(sl), coherent, tuple(sorted(fids.items())))
+        cached = self.__dict__.get("_source_rec_cache")
+        if cached is not None and cached[0] == key:
+            return cached[1], len(sl), aux_d
+        arr = (_cabi.OtbSource*max(len(sl), 1))()
         start = 0
         for k, (i, gid0, cnt) in enumerate(sl):
             r, S = recs[i], arr[k]
@@ -409,7 +416,8 @@ class Raytracer(Group):
             # measured: the numeric-surface kernels (CAPS_FULL) are bound by instruction fetch and lose with warps that
             # run different iteration counts side by side (cosine_surfaces 11.6 -> 14.7 ms): coherent order only for
             # scenes of flat and conic surfaces
-            S.coherent = int(bool(self.coherent_bundles) and scene_caps_lean(scene))
+            S.coherent = coherent
+        object.__setattr__(self, "_source_rec_cache", (key, arr))
         return arr, len(sl), aux_d
 
     def _generate(self, N_list, begin, end: int, seed: int, scene=None):

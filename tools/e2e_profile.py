@@ -20,10 +20,11 @@ prev = None
 def step():
     global prev
     RT.upload_every_trace = True
+    RT.deferred_status = True
     RT.trace(N)
+    out = prev._materialise() if prev is not None else None
     im = RT.detector_image()
     im.download_async()
-    out = prev._materialise() if prev is not None else None
     prev = im
     return out
 

@@ -22,11 +22,11 @@ def step():
     RT.upload_every_trace = mode == "e2e"
     RT.deferred_status = mode == "e2e"
     RT.trace(N)
+    if mode == "e2e" and prev is not None:
+        prev._materialise()
     im = RT.detector_image()
     if mode == "e2e":
         im.download_async()
-        if prev is not None:
-            prev._materialise()
     prev = im
 
 

@@ -11,6 +11,8 @@ from __future__ import annotations
 import ctypes as C
 from enum import IntEnum
 
+import sys
+
 import numpy as np
 
 from . import _cabi, dist, engine
@@ -524,8 +526,21 @@ class Raytracer(Group):
     def _run_trace(self, scene, rays, N_list, N_global, begin):
         # drop the previous ray storage first: its device blocks go back to the caching allocator and the new
         # store (same size on a repeated trace) reuses them instead of a fresh cudaMalloc of many GB
+        # When nobody but this tracer can still see the previous RayStorage, its device planes are overwritten in
+        # place by the new trace (same ray count and section count): returning 8 GB to the caching allocator and asking
+        # for them again makes every change of the set of live tensors (an image kept, a pipeline drained) a candidate
+        # for a synchronous multi-GB cudaMalloc (8-400 ms measured).  A RayStorage somebody else holds keeps its planes.
+        old = self.rays
+        recycled = None
+        if sys.getrefcount(old) <= 3:                       # self.rays, `old`, the argument of getrefcount
+            dev_store = old.__dict__.get("_dev")
+            if dev_store is not None and sys.getrefcount(dev_store) <= 3 and \
+                    (dev_store.N, dev_store.nt, dev_store.no_pol) == (rays.N, scene.nt, scene.flat.no_pol):
+                recycled = dev_store
+        del old
         self.rays = RayStorage()
-        store, msgs, status = engine.trace_store(scene, rays, sync=False)
+        store, msgs, status = engine.trace_store(scene, rays, store=recycled, sync=False)
+        recycled = None
         gen_status = getattr(rays, "gen_status", None)
         if gen_status is not None:
             status = status | gen_status

@@ -275,3 +275,22 @@ def test_deferred_status_collects_messages_at_the_detector_call(ot):
     assert RT3.__dict__.get("_pending_trace") is not None
     with pytest.raises(RuntimeError):
         RT3.finish_trace()
+
+
+def test_ray_store_is_recycled_only_when_unobservable(ot):
+    """a repeated trace overwrites the previous device planes in place (no 8 GB allocator round trip) unless the
+    caller still holds the previous RayStorage: that one keeps its data"""
+    g = gu.load("double_gauss")
+    p0, s0, pol0, w0, wl, hz = gu.bundle(g)
+    RT = scenes.SCENES["double_gauss"](ot)
+    RT.trace_rays(p0, s0, pol0, w0, wl, N_list=g["N_list"])
+    ptr1 = RT.rays._dev.p.data_ptr()
+    ref_p = RT.rays.p_list.copy()
+    RT.trace_rays(p0, s0, pol0, w0, wl, N_list=g["N_list"])
+    assert RT.rays._dev.p.data_ptr() == ptr1                      # recycled: nobody else could see the old storage
+    assert np.array_equal(RT.rays.p_list, ref_p)
+    held = RT.rays                                                   # the caller keeps the storage of this trace ...
+    RT.trace_rays(p0 + np.array([1e-3, 0, 0]), s0, pol0, w0, wl, N_list=g["N_list"])
+    assert RT.rays._dev.p.data_ptr() != held._dev.p.data_ptr()     # ... so the next trace got planes of its own
+    assert not np.array_equal(RT.rays.p_list, ref_p)
+    assert np.array_equal(held.p_list, ref_p)                       # and the held storage still has its data

@@ -529,7 +529,10 @@ def run_gpu(args):
                                   "image download of step k overlaps the trace of step k+1 (depth 1); only the occupied "
                                   "32 x 32 tiles of the histogram travel (otb_tiles.cu), over NVLink and over PCIe; "
                                   "N > 1: the all-reduced image is read back on rank 0"},
-            "gpu_launches": 8*args.steps,     # generate, trace_store, detector_hits, render x (resident + e2e region)
+            # this repo's kernels inside the two timed regions, per step: generate, trace_store, detector_hits, render
+            # (+ tiles_mask, tiles_pack for the download in the e2e region; N > 1: + tiles_mask, tiles_pack, tiles_unpack
+            # of the image reduce in both regions, reused by the download)
+            "gpu_launches": (10 if world == 1 else 14)*args.steps,
             "clocks": clk,
         }
         if not args.no_cpu and world == 1:

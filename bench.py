@@ -51,7 +51,9 @@ def parse():
     ap.add_argument("--no-compare", action="store_true", help="skip timing the other engine build")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not run the nvidia-smi clock sampler")
     ap.add_argument("--keep-gc", action="store_true", help="diagnostic: leave Python's cyclic garbage collector running in the timed regions")
-    ap.add_argument("--gc-log", action="store_true", help="diagnostic: report garbage collector pauses on stderr")
+    ap.add_argument("--diag", "--gc-log", dest="gc_log", action="store_true",
+                    help="diagnostic: per-step host times of both timed regions, phases of the slowest e2e step and garbage "
+                         "collector pauses on stderr")
     return ap.parse_args()
 
 

@@ -50,7 +50,6 @@ def parse():
                          "scene-specialised variant of Raytracer.compile()")
     ap.add_argument("--no-compare", action="store_true", help="skip timing the other engine build")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not run the nvidia-smi clock sampler")
-    ap.add_argument("--keep-gc", action="store_true", help="diagnostic: leave Python's cyclic garbage collector running in the timed regions")
     ap.add_argument("--diag", "--gc-log", dest="gc_log", action="store_true",
                     help="diagnostic: per-step host times of both timed regions, phases of the slowest e2e step and garbage "
                          "collector pauses on stderr")
@@ -333,10 +332,8 @@ def run_gpu(args):
     if rank == 0:
         clocks.wait_first()
         clocks.mark()
-    # A generation-2 pass of Python's cyclic garbage collector walks every object torch and numpy created at import
-    # (~1e6) and takes 50-100 ms: inside a 100 ms timed region it doubles ms_per_step (seen in one of four runs).
-    # Everything alive after the warm-up is moved to the permanent generation and the collector pauses while the
-    # steps are timed; the steps themselves create no reference cycles worth collecting.
+    # --diag: garbage collector passes inside the timed regions are logged (none above 0.2 ms was ever seen; the 2x
+    # outliers this diagnostic was written for turned out to be cudaMalloc stalls, see the warm-up above)
     gc_pauses = []
     if args.gc_log:
         _t = [0.0]
@@ -346,10 +343,6 @@ def run_gpu(args):
             else:
                 gc_pauses.append((info["generation"], (time.perf_counter() - _t[0])*1e3))
         gc.callbacks.append(_gc_cb)
-    if not args.keep_gc:
-        gc.collect()
-        gc.freeze()
-        gc.disable()
     t0, t1 = ev(), ev()
     t0.record()
     step_wall = []
@@ -449,7 +442,6 @@ def run_gpu(args):
     t1.record()
     barrier()
     e2e_ms = max(t0.elapsed_time(t1), (time.perf_counter() - w0)*1e3)/args.steps
-    gc.enable()
     if args.gc_log and rank == 0:
         d = np.diff(np.array(step_wall))*1e3
         print(f"[bench] host time between the returns of consecutive resident steps (ms): {np.round(d, 2).tolist()}", file=sys.stderr)

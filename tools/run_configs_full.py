@@ -51,8 +51,13 @@ def report(name, N, nt, t, extra):
 def store_mode(name, scene, N, dets=(0,)):
     RT = scenes.SCENES[scene](ot)
     nt = len(RT.tracing_surfaces) + 2
-    RT.trace(N)                                 # warm-up at full size (allocator growth, tables, image sources)
-    [RT.detector_image(d).power() for d in dets]
+    # two warm-up passes at full size with the timed pass's pattern of live tensors (images held while the next trace
+    # runs): allocator growth, tables, image sources; a changed live set costs the next pass a synchronous cudaMalloc
+    ims = None
+    for _ in range(2):
+        RT.trace(N)
+        ims = [RT.detector_image(d) for d in dets]
+        [im.power() for im in ims]
     sync()
     t0 = time.perf_counter()
     RT.trace(N)

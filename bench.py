@@ -212,10 +212,10 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
-        """Started BEFORE the warm-up: nvidia-smi's own start-up (NVML initialisation, enumeration of every GPU of
-        the box) holds driver locks for up to a second and stalls kernel launches of this process while it lasts —
-        inside the timed region it doubled ms_per_step on some boxes (5.3 -> 12.4 ms).  mark() opens the window whose
-        samples are reported (the timed regions); the polling itself (one NVML query per 100 ms) is harmless."""
+        """Started BEFORE the warm-up, so that nvidia-smi's own start-up (NVML initialisation, enumeration of every GPU
+        of the box) lies outside the timed regions; mark() opens the window whose samples are reported (the timed
+        regions); the polling itself is one NVML query per 100 ms.  (A/B runs with --no-clocks show no effect of the
+        sampler on the timings.)"""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)

@@ -129,7 +129,8 @@ __device__ __forceinline__ void store_step(const KScene& sc, const TraceArgs& a,
 
 // GEN: the rays are drawn inside the kernel (fused RaySource.create_rays).  A template parameter, not a run-time
 // branch: the generator is ~5000 instructions, and the kernels of injected / pre-generated bundles (the default) are
-// sensitive to their code footprint (cosine_surfaces: 8.9 ms without, 16 ms with the generator compiled in).
+// sensitive to their code footprint (measured on the fused render kernel, where only this changed: 6-detector bin
+// pass 1.87 -> 1.58 ms per 10 M rays; cosine_surfaces 12.2 -> 9.5 ms together with the out-of-line height functions).
 // THREADS: block size the register allocation is made for (see above; measured on hurb_square / hurb_pinhole:
 // 384 threads 2.27 / 1.78 ms, 512 threads 2.43 / 2.04 ms per 10 M rays — the opposite of the numeric-surface scenes).
 template <bool POL, int CAPS, bool GEN, int THREADS>

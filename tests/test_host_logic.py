@@ -333,3 +333,16 @@ def test_reference_gaussian_filter_weights_depend_on_the_hosts_simd_level():
     assert (here != base).mean() > 0.05            # the reference's own numbers differ between the two hosts ...
     assert 5e-8 < rel.max() < 3e-7                 # ... by up to ~2 float32 ulp: W_RTOL = 3e-7 covers exactly that
     assert (engine_rule != base).mean() < 1e-2     # the engine's rule IS the baseline loop up to rare last-bit ties
+
+
+def test_shared_split_cache_hands_out_copies():
+    """dist.shared_split caches the deterministic split of (N, powers); callers may modify what they get"""
+    import numpy as np
+    from optrace_b200 import dist
+    from optrace_b200.ray_storage import split_rays
+    a = dist.shared_split(1000, [1.0, 3.0], None)
+    assert a.tolist() == split_rays(1000, [1.0, 3.0]).tolist() == [250, 750]
+    a[0] = -1
+    b = dist.shared_split(1000, [1.0, 3.0], None)
+    assert b.tolist() == [250, 750]
+    assert dist.shared_split(1000, [3.0, 1.0], None).tolist() == [750, 250]      # another key, not the cached one
